@@ -1,0 +1,448 @@
+"""Generate the golden fixtures in this directory from the UNMODIFIED reference.
+
+Run in the build container only (``/root/reference`` is read-only and does not
+exist on the GPU box):
+
+    python tests/golden/gen_golden.py [case ...]
+
+Nothing is copied from the reference: its modules are imported from where they
+lie and driven through their public classes; only numeric outputs are stored
+(compressed ``.npz``).  Two load-time shims, both in memory:
+
+  * ``ndarray.itemset((i, j), v)`` (removed in NumPy 2) is rewritten to index
+    assignment in ``hamil_2d.py`` / ``task_manager.py`` before ``exec``;
+  * ``test_data/*.py`` golden tables are loaded by file path because
+    ``test_data/__init__.py`` imports files that are absent from the mount.
+"""
+from __future__ import annotations
+
+import contextlib
+import copy
+import importlib.util
+import io
+import os
+import re
+import sys
+import types
+
+import numpy as np
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load_reference():
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    shim = re.compile(r"(\w+)\.itemset\(\((.+?),\s*(.+?)\),\s*(.+)\)\s*(#.*)?$", re.M)
+
+    def load_shimmed(name):
+        src = open(os.path.join(REF, name + ".py")).read()
+        src = shim.sub(lambda m: "%s[%s, %s] = %s" % (m.group(1), m.group(2), m.group(3), m.group(4)), src)
+        assert "itemset" not in src, name
+        mod = types.ModuleType(name)
+        mod.__file__ = os.path.join(REF, name + ".py")
+        sys.modules[name] = mod
+        exec(compile(src, mod.__file__, "exec"), mod.__dict__)
+        return mod
+
+    import math_base, phys_base, psi_basis  # noqa: F401
+    load_shimmed("hamil_2d")
+    import propagation  # noqa: F401
+    load_shimmed("task_manager")
+    import fitter, config, reporter  # noqa: F401
+    return types.SimpleNamespace(**{k: sys.modules[k] for k in
+                                    ("math_base", "phys_base", "psi_basis", "hamil_2d", "propagation",
+                                     "task_manager", "fitter", "config", "reporter")})
+
+
+def load_table(name):
+    spec = importlib.util.spec_from_file_location("td_" + name, os.path.join(REF, "test_data", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@contextlib.contextmanager
+def quiet():
+    with contextlib.redirect_stdout(io.StringIO()):
+        yield
+
+
+def psi_arr(psi):
+    return np.stack([np.asarray(f, np.complex128) for f in psi.f])
+
+
+def basis_arr(basis):
+    return np.stack([psi_arr(p) for p in basis.psis])
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote %-40s %8.1f kB" % (name + ".npz", os.path.getsize(path) / 1e3))
+
+
+# ----------------------------------------------------------------------------
+# configurations (same dictionaries the reference's functional tests use,
+# tests/functional_tests.py:77-1164, with nt reduced and T scaled so that the
+# time step - hence t_sc and the interpolation coefficients - is unchanged)
+# ----------------------------------------------------------------------------
+def conf_single_harm(nt):
+    return {"task_type": "single_pot", "pot_type": "harmonic", "wf_type": "harmonic", "hamil_type": "ntriv",
+            "init_guess": "zero", "nb": 1, "nlevs": 2, "T": 280e-15 * nt / 200000, "L": 10.0, "np": 512,
+            "a": 1.0, "x0p": 0.0, "a_e": 0.0, "De_e": 0.0, "Du": 0.0, "x0": 1.0, "p0": 0.0,
+            "fitter": {"impulses_number": 0, "mod_log": 500,
+                       "propagation": {"m": 0.5, "nch": 64, "nt": nt, "E0": 0.0, "nu_L": 0.0}}}
+
+
+def conf_single_morse(nt):
+    return {"task_type": "single_pot", "pot_type": "morse", "wf_type": "harmonic", "hamil_type": "ntriv",
+            "init_guess": "zero", "nb": 1, "nlevs": 2, "T": 280e-15 * nt / 200000, "L": 4.0, "np": 2048,
+            "a": 1.0, "De": 20000.0, "x0p": 0.0, "a_e": 0.0, "De_e": 0.0, "Du": 0.0, "x0": 0.0, "p0": 0.0,
+            "fitter": {"impulses_number": 0, "mod_log": 500,
+                       "propagation": {"m": 0.5, "nch": 64, "nt": nt, "E0": 0.0, "nu_L": 0.0}}}
+
+
+def conf_trans_woc(nt, t0=None):
+    T = 330e-15 * nt / 230000
+    return {"task_type": "trans_wo_control", "pot_type": "morse", "wf_type": "morse", "hamil_type": "ntriv",
+            "init_guess": "gauss", "init_guess_hf": "exp", "nb": 1, "nlevs": 2, "T": T, "L": 5.0, "np": 1024,
+            "a": 1.0, "De": 20000.0, "x0p": -0.17, "a_e": 1.0, "De_e": 10000.0, "Du": 20000.0,
+            "fitter": {"impulses_number": 1, "mod_log": 500,
+                       "propagation": {"m": 0.5, "nch": 64, "nt": nt, "E0": 71.54,
+                                       "t0": T / 2 if t0 is None else t0, "sigma": T / 6, "nu_L": 0.29297e15}}}
+
+
+def conf_krotov(nt, iter_max, np_=1024):
+    T = 350e-15 * nt / 230000
+    return {"task_type": "optimal_control_krotov", "pot_type": "morse", "wf_type": "morse", "hamil_type": "ntriv",
+            "init_guess": "gauss", "init_guess_hf": "exp", "nb": 1, "nlevs": 2, "T": T, "L": 5.0, "np": np_,
+            "a": 1.0, "De": 20000.0, "x0p": -0.17, "a_e": 1.0, "De_e": 10000.0, "Du": 20000.0,
+            "fitter": {"epsilon": 1e-8, "impulses_number": 1, "iter_max": iter_max, "h_lambda": 0.0066,
+                       "mod_log": 500,
+                       "propagation": {"m": 0.5, "nch": 64, "nt": nt, "E0": 71.54 * 40, "t0": T / 2, "sigma": T / 6,
+                                       "nu_L": 0.29297e15}}}
+
+
+def conf_ut_jx(nt, iter_max, nlevs=2, w_list=(1.5, -1.0, 0.7999999999999998), T=5.4e-13):
+    return {"task_type": "optimal_control_unit_transform", "pot_type": "none", "wf_type": "const",
+            "hamil_type": "BH_model", "lf_aug_type": "x", "init_guess": "sqrsin", "init_guess_hf": "sin_set",
+            "nb": nlevs, "nlevs": nlevs, "T": T, "np": 1, "L": 1.0, "Du": 1.0, "U": 30.0, "W": 30.0, "delta": 15.0,
+            "sigma_auto": True, "nu_L_auto": True,
+            "fitter": {"epsilon": 1e-5, "impulses_number": 1, "iter_max": iter_max, "iter_mid_1": 250,
+                       "iter_mid_2": 300, "q": 0.75, "h_lambda": 0.00005, "h_lambda_mode": "dynamical",
+                       "pcos": 2.0, "hf_hide": False, "w_list": list(w_list), "mod_log": 500,
+                       "propagation": {"nch": 8, "t0": 0.0, "E0": 40.0, "nt": nt}}}
+
+
+def conf_ut_jz(nt, iter_max):
+    return {"task_type": "optimal_control_unit_transform", "pot_type": "none", "wf_type": "const",
+            "hamil_type": "BH_model", "lf_aug_type": "z", "init_guess": "sqrsin", "init_guess_hf": "cos_set",
+            "nb": 2, "nlevs": 2, "T": 3.306555E-13, "np": 1, "L": 1.0, "Du": 1.0, "U": 5.0, "delta": 25.0,
+            "fitter": {"epsilon": 1e-8, "impulses_number": 1, "iter_max": iter_max, "h_lambda": 0.005,
+                       "hf_hide": False, "w_list": [0.88, 0.34, 0.92, 0.27, 0.39, 0.82, 0.68], "pcos": 4.0,
+                       "Em": 5.0, "mod_log": 500,
+                       "propagation": {"nch": 8, "t0": 0.0, "E0": 40.0, "nt": nt, "sigma": 6.671270E-13,
+                                       "nu_L": 0.299793E14}}}
+
+
+def conf_ut_s2s(nt, iter_max):
+    return {"task_type": "optimal_control_unit_transform", "pot_type": "none", "wf_type": "const",
+            "hamil_type": "BH_model", "lf_aug_type": "x", "init_guess": "gauss", "init_guess_hf": "exp",
+            "nb": 1, "nlevs": 2, "T": 2.779700E-13, "np": 1, "L": 1.0, "Du": 1.0, "U": 30.0, "W": 30.0,
+            "delta": 15.0, "sigma_auto": True, "nu_L_auto": True, "t0_auto": True,
+            "fitter": {"epsilon": 1e-6, "impulses_number": 1, "iter_max": iter_max, "iter_mid_1": 30,
+                       "iter_mid_2": 50, "q": 0.75, "h_lambda": 0.00005, "h_lambda_mode": "dynamical",
+                       "F_type": "sm", "hf_hide": False, "pcos": 1.0, "mod_log": 500,
+                       "propagation": {"nch": 8, "E0": 40.0, "nt": nt}}}
+
+
+def conf_pi_pulse():
+    return {"task_type": "trans_wo_control", "pot_type": "none", "wf_type": "const", "hamil_type": "BH_model",
+            "lf_aug_type": "x", "init_guess": "const", "init_guess_hf": "exp", "nb": 1, "nlevs": 2,
+            "T": 555.9416E-15, "np": 1, "L": 1.0, "Du": 1.0, "U": 30.0, "W": 0.0, "delta": 15.0,
+            "fitter": {"epsilon": 1e-5, "impulses_number": 1, "iter_max": 300, "iter_mid_1": 250,
+                       "iter_mid_2": 300, "q": 0.75, "h_lambda": 0.00005, "h_lambda_mode": "const",
+                       "F_type": "sm", "pcos": 1.0, "hf_hide": False, "mod_log": 500,
+                       "propagation": {"nch": 8, "t0": 0.0, "E0": 1.0, "nt": 512, "nu_L": 0.00179875E15}}}
+
+
+CONFIGS = {
+    "single_harm": conf_single_harm, "single_morse": conf_single_morse, "trans_woc": conf_trans_woc,
+    "krotov": conf_krotov, "ut_jx": conf_ut_jx, "ut_jz": conf_ut_jz, "ut_s2s": conf_ut_s2s,
+    "pi_pulse": conf_pi_pulse,
+}
+
+
+# ----------------------------------------------------------------------------
+# recording reporters (the reference's own test doubles are in tests/test_tools.py;
+# these do the same job but keep every step and copy the arrays)
+# ----------------------------------------------------------------------------
+def make_reporters(R, every=1):
+    class PropRec(R.reporter.PropagationReporter):
+        def __init__(self, nlevs):
+            super().__init__("", nlevs)
+            self.rows = []
+
+        def open(self):
+            return self
+
+        def close(self):
+            pass
+
+        def print_time_point_prop(self, l, psi, t, x, np_, nt, moms, smoms, ener, norm, overlp0, overlpf,
+                                  overlp_tot, ener_tot, psi_max_abs, psi_max_real, E, freq_mult):
+            if l % every:
+                return
+            self.rows.append(dict(
+                l=l, t=t, psi=psi_arr(psi).copy(), momx=np.array(moms.x), momx2=np.array(moms.x2),
+                momp=np.array(moms.p), momp2=np.array(moms.p2), ener=np.array(ener), norm=np.array(norm),
+                overlp0=np.array(overlp0), overlpf=np.array(overlpf), E=complex(E), freq_mult=float(freq_mult),
+                ener_tot=complex(ener_tot), smoms=np.array([smoms.x, smoms.y, smoms.z], np.complex128),
+                psi_max_abs=np.array(psi_max_abs), psi_max_real=np.array(psi_max_real)))
+
+    class FitRec(R.reporter.FitterReporter):
+        def __init__(self):
+            super().__init__()
+            self.iters = []
+            self.props = {}
+
+        def open(self):
+            return self
+
+        def close(self):
+            pass
+
+        def print_iter_point_fitter(self, it, goal_close, E_tlist, t_list, Fsm, E_int, J, nt):
+            self.iters.append((it, float(goal_close), float(np.real(Fsm)), float(np.real(E_int)), float(J),
+                               np.array(E_tlist, np.float64)))
+
+        def create_propagation_reporter(self, prop_id, nlevs):
+            r = PropRec(nlevs)
+            self.props[prop_id] = r
+            return r
+
+    return PropRec, FitRec
+
+
+def run_fitter(R, user_conf, every=1, patch=None):
+    """Drive TaskRootConfiguration -> task_manager.create -> FittingSolver the way
+    tests/functional_tests.py:20-27,120-133 do.  ``patch(conf, tm)`` may adjust
+    the task manager's products (used for pi_pulse, functional_tests.py:29-75)."""
+    _, FitRec = make_reporters(R, every)
+    with quiet():
+        conf = R.config.TaskRootConfiguration()
+        conf.load(user_conf)
+        tm = R.task_manager.create(conf)
+        kw = dict(init_dir=tm.init_dir, ntriv=tm.ntriv, psi0=tm.psi0, psif=tm.psif, v=tm.v, akx2=tm.akx2,
+                  hamil2D=tm.hamil2D)
+        if patch:
+            patch(conf, tm, kw)
+        rep = FitRec()
+        fs = R.fitter.FittingSolver(conf.fitter, conf.task_type, conf.T, conf.np, conf.L, kw["init_dir"],
+                                    kw["ntriv"], kw["psi0"], kw["psif"], kw["v"], kw["akx2"], tm.F_goal,
+                                    tm.laser_field, tm.laser_field_hf, tm.F_type, tm.aF_type, kw["hamil2D"],
+                                    rep, None, None)
+        err = ""
+        try:
+            fs.time_propagation(tm.dx, tm.x, tm.t_step, tm.t_list)
+        except ValueError as e:          # divergence guard, fitter.py:550-560
+            err = str(e)
+    return conf, tm, fs, rep, err
+
+
+def pack_fitter(rep, fs, tm, err="", keep_psi=()):
+    out = {}
+    its = rep.iters
+    out["iter_tab"] = np.array([r[:5] for r in its], np.float64)
+    out["iter_E"] = np.stack([r[5] for r in its]) if its else np.zeros((0, 0))
+    out["error"] = np.array(err)
+    out["psi0"] = basis_arr(tm.psi0)
+    out["psif"] = basis_arr(tm.psif)
+    out["v"] = np.stack([np.asarray(vv[1], np.float64) for vv in tm.v])
+    out["vmin"] = np.array([float(vv[0]) for vv in tm.v])
+    out["akx2"] = np.asarray(tm.akx2)
+    out["x"] = np.asarray(tm.x)
+    out["dx"] = np.float64(tm.dx)
+    out["t_step"] = np.float64(tm.t_step)
+    for pid in keep_psi:
+        rows = rep.props[pid].rows
+        key = pid.replace("/", "__")
+        out[key + "__l"] = np.array([r["l"] for r in rows])
+        out[key + "__t"] = np.array([r["t"] for r in rows])
+        out[key + "__E"] = np.array([r["E"] for r in rows])
+        out[key + "__psi"] = np.stack([r["psi"] for r in rows])
+        for f in ("ener", "norm", "overlp0", "overlpf", "momx", "momx2", "momp", "momp2", "psi_max_abs",
+                  "psi_max_real", "smoms"):
+            out[key + "__" + f] = np.stack([np.asarray(r[f]) for r in rows])
+    return out
+
+
+# ----------------------------------------------------------------------------
+# cases
+# ----------------------------------------------------------------------------
+def case_kat(R):
+    """Reference unit-test vectors, recomputed by the reference itself and
+    stored beside the literals of tests/math_base_tests.py:19-51."""
+    mb, pbm = R.math_base, R.phys_base
+    out = {}
+    for nch in (2, 4, 8, 64):
+        out["reorder_%d" % nch] = np.array(mb.reorder(nch))
+    for nch, t in ((4, 1.0), (8, 5.65e-3), (8, -5.65e-3), (64, 0.2040), (64, 3.737), (64, -3.737), (64, 20.55)):
+        xp, dv = mb.points(nch, t, pbm.func)
+        tag = "points_%d_%s" % (nch, repr(t).replace("-", "m").replace(".", "p"))
+        out[tag + "_xp"] = xp
+        out[tag + "_dv"] = dv
+    out["initak_4"] = mb.initak(4, 0.2, 2, 1)
+    out["initak_16_o1"] = mb.initak(16, 0.3, 1, 1)
+    out["initak_8_triv"] = mb.initak(8, 0.3, 2, -2)
+    save("kat_math_base", **out)
+
+
+def case_one_step(R):
+    """phys_base.prop_cpu on a non-trivial state for the three grid configs
+     and both time directions."""
+    P = R.propagation.PropagationSolver
+    for name, user, warm in (("harm", conf_single_harm(2000), 40), ("morse", conf_single_morse(2000), 40),
+                             ("krotov", conf_krotov(2000, 1), 700)):
+        _, FitRec = make_reporters(R)
+        with quiet():
+            conf = R.config.TaskRootConfiguration()
+            conf.load(user)
+            tm = R.task_manager.create(conf)
+        # warm the state up with the reference's own stepper so both levels are populated
+        cp = conf.fitter.propagation
+
+        def env(prop, stat, dyn, _E0=float(cp.E0)):
+            return np.float64(_E0 * 0.37) if name == "krotov" else np.float64(0.0)
+
+        def factory(l, t, psi, psi_omega, E, fm, d):
+            return P.DynamicState(l, t, copy.deepcopy(psi), copy.deepcopy(psi_omega), E, fm, d)
+
+        class Null(R.reporter.PropagationReporter):
+            def __init__(self):
+                super().__init__("", 2)
+
+            def open(self):
+                return self
+
+            def close(self):
+                pass
+
+            def print_time_point_prop(self, *a):
+                pass
+
+        with quiet():
+            s = P(T=conf.T, np=conf.np, L=conf.L, _warning_collocation_points=None, _warning_time_steps=None,
+                  reporter=Null(), hamil2D=tm.hamil2D, laser_field_envelope=env,
+                  laser_field_hf=tm.laser_field_hf, freq_multiplier=lambda d, st: np.float64(1.0),
+                  dynamic_state_factory=factory, pcos=conf.fitter.pcos, w_list=conf.fitter.w_list,
+                  mod_log=10 ** 9, ntriv=tm.ntriv, hf_hide=conf.fitter.hf_hide, conf_prop=cp)
+            s.start(tm.v, tm.akx2, tm.dx, tm.x, tm.t_step, tm.psi0.psis[0], tm.psif.psis[0], P.Direction.FORWARD)
+            for _ in range(warm):
+                s.step(0.0)
+        state = s.dyn.psi_omega if conf.fitter.hf_hide else s.dyn.psi
+        psi_in = psi_arr(state).copy()
+        emax, emin, t_sc = float(s.instr.emax), float(s.instr.emin), float(s.instr.t_sc)
+        eL = float(cp.nu_L * R.phys_base.Hz_to_cm / 2.0)
+        out = dict(psi_in=psi_in, emax=emax, emin=emin, t_sc=t_sc, eL=eL, dx=np.float64(tm.dx),
+                   v=np.stack([np.asarray(vv[1]) for vv in tm.v]), akx2=np.asarray(tm.akx2), nch=np.int64(cp.nch))
+        for tag, E, sign in (("f", 0.0 if name != "krotov" else 31.7, 1.0), ("b", 0.0 if name != "krotov" else -12.5, -1.0)):
+            psi = R.psi_basis.Psi(f=[psi_in[0].copy(), psi_in[1].copy()], lvls=2)
+            res = R.phys_base.prop_cpu(psi=psi, hamil2D=tm.hamil2D, t_sc=sign * t_sc, nch=cp.nch, np=conf.np,
+                                       emin=emin, emax=emax, E=np.float64(E), eL=eL, E_full=np.float64(E), orig=False)
+            out["psi_out_" + tag] = psi_arr(res)
+            out["E_" + tag] = np.float64(E)
+        # one Hamiltonian application, both forms
+        psi = R.psi_basis.Psi(f=[psi_in[0].copy(), psi_in[1].copy()], lvls=2)
+        out["hpsi_shift"] = psi_arr(tm.hamil2D(False, psi, np.float64(3.3), eL, np.complex128(3.3)))
+        out["hpsi_orig"] = psi_arr(tm.hamil2D(True, psi, np.float64(3.3), eL, np.complex128(1.2 - 0.7j)))
+        save("one_step_" + name, **out)
+
+
+def case_fitter_grid(R):
+    """Full FittingSolver runs on the FFT grid with reduced nt: prescribed-field
+    tasks and Krotov iterations (forward/backward sweeps + field updates)."""
+    for name, user, every, keep in (
+            ("fit_single_harm", conf_single_harm(60), 10, ("iter_0f/basis_0",)),
+            ("fit_single_morse", conf_single_morse(40), 10, ("iter_0f/basis_0",)),
+            ("fit_trans_woc", conf_trans_woc(300), 50, ("iter_0f/basis_0",)),
+            ("fit_krotov_1024", conf_krotov(240, 2), 60, ("iter_0f/basis_0", "iter_0b/basis_0", "iter_1f/basis_0",
+                                                          "iter_2f/basis_0")),
+            ("fit_krotov_256", conf_krotov(120, 3, np_=256), 40, ("iter_0f/basis_0", "iter_3f/basis_0"))):
+        conf, tm, fs, rep, err = run_fitter(R, user, every)
+        out = pack_fitter(rep, fs, tm, err, keep)
+        out["conf_json"] = np.array(repr(user))
+        save(name, **out)
+
+
+def case_fitter_nlevel(R):
+    """Unitary-transformation control on N-level systems (np = 1)."""
+    def pi_patch(conf, tm, kw):            # tests/functional_tests.py:29-75
+        tmod = R.task_manager
+        cp = conf.fitter.propagation
+        psi0 = R.psi_basis.PsiBasis(1)
+        psi0.psis[0].f[0] = tmod._PsiFunctions.one(tm.x, conf.np, conf.x0, conf.p0, cp.m, conf.De, conf.a, conf.L)
+        psi0.psis[0].f[1] = tmod._PsiFunctions.zero(conf.np)
+        psif = R.psi_basis.PsiBasis(1)
+        psif.psis[0].f[0] = tmod._PsiFunctions.zero(conf.np)
+        psif.psis[0].f[1] = tmod._PsiFunctions.one(tm.x, conf.np, conf.x0p + conf.x0, conf.p0, cp.m, conf.De_e,
+                                                   conf.a_e, conf.L)
+        kw.update(psi0=psi0, psif=psif, ntriv=-2, init_dir=R.propagation.PropagationSolver.Direction.FORWARD,
+                  hamil2D=R.hamil_2d.Hamil2DQubit(tm.v, tm.akx2, conf.np, conf.U, conf.W, conf.delta, -2))
+        tm.psi0, tm.psif = psi0, psif
+
+    for name, user, every, keep, patch in (
+            ("fit_ut_jx", conf_ut_jx(400, 3), 100, ("iter_0b/basis_0", "iter_0f/basis_1", "iter_3f/basis_0"), None),
+            ("fit_ut_jx_4lvls", conf_ut_jx(300, 2, nlevs=4, w_list=(0.3, 1.1, -0.6)), 100, ("iter_2f/basis_3",), None),
+            ("fit_ut_jz", conf_ut_jz(350, 3), 50, ("iter_3f/basis_1",), None),
+            ("fit_ut_s2s", conf_ut_s2s(350, 3), 50, ("iter_3f/basis_0",), None),
+            ("fit_pi_pulse", conf_pi_pulse(), 64, ("iter_0f/basis_0",), pi_patch)):
+        conf, tm, fs, rep, err = run_fitter(R, user, every, patch)
+        out = pack_fitter(rep, fs, tm, err, keep)
+        out["conf_json"] = np.array(repr(user))
+        save(name, **out)
+
+
+def case_shipped(R):
+    """Rows of the reference's shipped golden tables (test_data/*.py), stored as
+    arrays so they can be checked on the GPU box."""
+    out = {}
+    for fam in ("opt_ctrl_ut_HB_2lvls_Jx", "pi_pulse"):
+        td = load_table("fit_iter_" + fam)
+        out[fam + "__iter_tab"] = np.array(td.iter_tab, np.float64)
+        out[fam + "__iter_E"] = np.array([r[2] for r in td.iter_tab_E], np.float64)
+        out[fam + "__iter_t"] = np.array(td.iter_tab_E[0][1], np.float64)
+    for fam in ("opt_ctrl_ut_HB_2lvls_Jx", "opt_ctrl_ut_HB_2lvls_Jz", "opt_ctrl_ut_HB_s2s_Jx", "pi_pulse",
+                "single_harm", "single_morse", "trans_woc", "opt_ctrl_krot", "filter", "int_ctrl"):
+        td = load_table("fitter_" + fam)
+        out[fam + "__tvals"] = np.array([[complex(c) for c in row] for row in td.tvals_tab], np.complex128)
+    td = load_table("fit_iter_single_morse")
+    out["single_morse__iter_tab"] = np.array(td.iter_tab, np.float64)
+    for fam in ("opt_ctrl_ut_HB_2lvls_Jx", "opt_ctrl_ut_HB_2lvls_Jz", "opt_ctrl_ut_HB_s2s_Jx", "pi_pulse"):
+        td = load_table("prop_" + fam)
+        for n, tab in enumerate(td.prop_tabs):
+            out["%s__prop_l%d" % (fam, n)] = np.array([[complex(c) for c in row] for row in tab], np.complex128)
+    save("shipped_tables", **out)
+    # grid wavefunctions: first records of the forward/backward 230000-step runs
+    # (tests/unit_tests_propagation.py:115-271); records are every 10000 steps.
+    out = {}
+    for fam, nrec in (("trans_woc_forw", 3), ("trans_woc_back", 3), ("opt_ctrl_krot", 3)):
+        td = load_table("prop_" + fam)
+        for n in range(2):
+            out["%s__psi_l%d" % (fam, n)] = np.stack([np.asarray(td.psi_tabs[n][k][0], np.complex128)
+                                                     for k in range(nrec)])
+            out["%s__t" % fam] = np.array([td.psi_tabs[n][k][1] for k in range(nrec)])
+            out["%s__prop_l%d" % (fam, n)] = np.array([[complex(c) for c in row] for row in td.prop_tabs[n][:nrec]],
+                                                      np.complex128)
+    save("shipped_grid_records", **out)
+
+
+CASES = {"kat": case_kat, "one_step": case_one_step, "fitter_grid": case_fitter_grid,
+         "fitter_nlevel": case_fitter_nlevel, "shipped": case_shipped}
+
+if __name__ == "__main__":
+    R = load_reference()
+    for c in (sys.argv[1:] or list(CASES)):
+        CASES[c](R)
