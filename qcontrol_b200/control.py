@@ -1,0 +1,418 @@
+"""Batched control loops on the GPU engine.
+
+``GridBatch`` runs many independent two-level FFT-grid problems (prescribed
+field or Krotov optimal control) and ``NLevelBatch`` many N-level
+unitary-transformation problems, each batch as ONE plan: all sweeps of all runs
+are single kernel launches, the iteration logic stays on the host.  These
+classes restate the sweep bookkeeping of ``FittingSolver`` (fitter.py:213-571)
+for a whole batch; per run they produce the same iteration rows
+(iter, goal_close, Fsm, E_int, J) and field lists E_tlist.
+
+A "problem" is any object with the attributes produced by
+``qcontrol_b200.task_manager.create`` (psi0, psif, v, vmin, akx2, dx, T, nt,
+nch, E0, t0, sigma, nu_L, hf_hide, h_lambda, ... and the two callables
+``laser_field`` / ``laser_field_hf``).
+"""
+from __future__ import annotations
+
+import cmath
+import math
+from dataclasses import dataclass, field
+from typing import List, Sequence
+
+import numpy as np
+
+from . import engine as eng
+from . import math_base
+from .phys_consts import CM_TO_ERG, HZ_TO_CM, RED_PLANCK_H
+
+FORWARD, BACKWARD = 1, -1
+
+_HAMIL_CODE = {"ntriv": eng.HAMIL_NONTRIV, "two_levels": eng.HAMIL_TWO_LEVELS, "bh_x": eng.HAMIL_BH_X,
+               "bh_z": eng.HAMIL_BH_Z, "qubit": eng.HAMIL_QUBIT}
+
+
+@dataclass
+class IterRow:
+    it: int
+    goal_close: float
+    Fsm: float
+    E_int: float
+    J: float
+    E_tlist: np.ndarray
+
+
+def _F_value(kind, gc, nb):
+    """task_manager.py:162-207 on one run's goal-closeness vector."""
+    F = np.complex128(0)
+    if kind == "sm":
+        for a in range(nb):
+            for b in range(nb):
+                F -= gc[a] * gc[b].conjugate()
+    elif kind == "re":
+        for a in range(nb):
+            F -= gc[a].real
+    else:
+        for a in range(nb):
+            F -= gc[a] * gc[a].conjugate()
+    return F
+
+
+def _a_value(kind, psi_init, chi_init, dx):
+    """task_manager.py:209-268 (a_sm, a_re, a_ss) on one run."""
+    nb, nlevs, _ = psi_init.shape
+    a = np.zeros(nb, np.complex128)
+    if kind == "re":
+        a[:] = 0.5
+        return a
+    if kind == "sm":
+        for va in range(nb):
+            for v in range(nb):
+                for n in range(nlevs):
+                    a[va] += np.vdot(chi_init[v, n], psi_init[v, n]) * dx
+        return a
+    for v in range(nb):
+        for n in range(nlevs):
+            a[v] += np.vdot(chi_init[v, n], psi_init[v, n]) * dx
+    return a
+
+
+def energy_window(pb, direction=FORWARD, freq_mult=1.0):
+    """emax, emin, t_sc, eL of PropagationSolver.step (propagation.py:371-407)."""
+    extr = []
+    kmax = abs(pb.akx2[int(pb.np_ / 2 - 1)])
+    for n in range(pb.nlevs):
+        extr.append(pb.v[n][0] + kmax)
+        extr.append(pb.vmin[n])
+    eL = pb.nu_L * freq_mult * HZ_TO_CM / 2.0
+    if pb.hf_hide:
+        ext = [extr[0] + pb.E0 + eL, extr[1] - pb.E0 + eL, extr[2] + pb.E0 - eL, extr[3] - pb.E0 - eL]
+        emax, emin = max(ext), min(ext)
+    else:
+        emax, emin = max(extr), min(extr)
+    dt = direction * pb.t_step
+    t_sc = dt * (emax - emin) * CM_TO_ERG / 4.0 / RED_PLANCK_H
+    return emax, emin, t_sc, eL
+
+
+def step_times(pb, direction):
+    """dyn.t for l = 0..nt (propagation.py:354-357, 377)."""
+    nt = pb.nt
+    if direction == FORWARD:
+        t0 = np.float64(0.0)
+        dt = pb.t_step
+    else:
+        t0 = pb.T
+        dt = -pb.t_step
+    return [t0] + [dt * l + t0 for l in range(1, nt + 1)]
+
+
+class _BatchBase:
+    def __init__(self, problems: Sequence, ctx: eng.Context = None, device: int = 0, store_traj=True):
+        self.pbs = list(problems)
+        p0 = self.pbs[0]
+        self.B = len(self.pbs)
+        self.ctx = ctx or eng.Context(device)
+        for p in self.pbs:
+            assert (p.np_, p.nlevs, p.nb, p.nch, p.hamil, p.hf_hide) == \
+                   (p0.np_, p0.nlevs, p0.nb, p0.nch, p0.hamil, p0.hf_hide), "a batch shares one plan shape"
+        self.nt = np.array([p.nt for p in self.pbs])
+        self.nt_max = int(self.nt.max())
+        self.plan = eng.Plan(self.ctx, _HAMIL_CODE[p0.hamil], p0.np_, p0.nlevs, p0.nb, p0.nch, self.B, self.nt_max,
+                             hf_hide=p0.hf_hide, store_traj=store_traj)
+        self.psi0 = np.stack([p.psi0 for p in self.pbs])
+        self.psif = np.stack([p.psif for p in self.pbs])
+        self.dx = np.array([float(p.dx) for p in self.pbs])
+        self.plan.snapshot_set(0, self.psi0)      # SNAP_INIT
+        self.plan.snapshot_set(1, self.psif)      # SNAP_GOAL
+        self._upload_static()
+        self._poly_dir = {}
+        for slot, d in ((0, FORWARD), (1, BACKWARD)):
+            self._upload_poly(slot, d)
+
+    def _upload_poly(self, slot, direction):
+        emins, emaxs, tscs, eLs = [], [], [], []
+        for p in self.pbs:
+            emax, emin, t_sc, eL = energy_window(p, direction)
+            emins.append(emin); emaxs.append(emax); tscs.append(t_sc); eLs.append(eL)
+        nch = self.pbs[0].nch
+        if len(set(float(t) for t in tscs)) > 64:
+            xp, dvs = math_base.newton_tables_batched(nch, tscs)
+        else:
+            tabs = [math_base.newton_table(nch, t) for t in tscs]
+            xp, dvs = tabs[0][0], np.stack([t[1] for t in tabs])
+        self.plan.set_poly(slot, xp, dvs, np.array(emins), np.array(emaxs), np.array(tscs), np.array(eLs))
+        self._poly_dir[direction] = slot
+
+    def _pad(self, rows, dtype=np.complex128):
+        out = np.zeros((self.B, self.nt_max + 1), dtype)
+        for b, r in enumerate(rows):
+            out[b, :len(r)] = r
+        return out
+
+    def close(self):
+        self.plan.close()
+
+
+class GridBatch(_BatchBase):
+    """Two-level FFT-grid runs: prescribed-field propagation and Krotov optimal control."""
+
+    def _upload_static(self):
+        p0 = self.pbs[0]
+        self.plan.set_static(np.stack([p.v for p in self.pbs]), np.ascontiguousarray(p0.akx2.real), None, self.dx)
+        for p in self.pbs:
+            assert np.array_equal(p.akx2, p0.akx2), "one kinetic multiplier per batch"
+        if p0.hf_hide:
+            for slot, d in ((0, FORWARD), (1, BACKWARD)):
+                rows = []
+                for p in self.pbs:
+                    ts = step_times(p, d)
+                    rows.append([np.complex128(cmath.sqrt(p.laser_field_hf(np.float64(1.0), t, p.pcos, p.w_list)))
+                                 for t in ts])
+                self.plan.set_exp_L(self._pad(rows), slot)
+        self.plan.set_control(np.array([float(p.h_lambda) for p in self.pbs]), self.nt.astype(np.float64))
+
+    def _prescribed_field(self, p, direction):
+        """LaserFieldEnvelope / ...Backward for tasks without feedback (fitter.py:650-670, 809)."""
+        out = []
+        for t in step_times(p, direction):
+            if direction == BACKWARD or p.hf_hide:
+                E = p.laser_field(p.E0, t, p.t0, p.sigma)
+            else:
+                E = p.laser_field(p.E0, t, p.t0, p.sigma) * p.laser_field_hf(np.float64(1.0), t, p.pcos, p.w_list)
+            if direction == FORWARD and p.task_type == "intuitive_control":
+                for k in range(1, p.impulses_number):
+                    E += p.laser_field(p.E0, t, p.t0 + k * p.delay, p.sigma)
+            out.append(E)
+        return out
+
+    def propagate(self, direction=FORWARD, record=False, chunk=None, on_chunk=None):
+        """One prescribed-field sweep of every run from psi0 (forward) / psif (backward)."""
+        pl = self.plan
+        pl.snapshot_load(0 if direction == FORWARD else 1)
+        pl.set_E_base(self._pad([self._prescribed_field(p, direction) for p in self.pbs]))
+        slot = self._poly_dir[direction]
+        if record:
+            pl.record_state(0, 0, 0)
+        chunk = chunk or self.nt_max
+        l = 1
+        while l <= self.nt_max:
+            n = min(chunk, self.nt_max - l + 1)
+            pl.sweep(slot, eng.FIELD_PRESCRIBED, l, n, True, -1, 0 if record else -1)
+            l += n
+            if on_chunk:
+                on_chunk(l - 1)
+        return pl.get_state()
+
+    def _finish_forward(self, it, E0_start):
+        pl = self.plan
+        E = pl.get_fields()
+        gc = pl.goal_overlap(1)
+        rows = []
+        for b, p in enumerate(self.pbs):
+            Et = np.array([E0_start[b]] + [E[b, l] for l in range(1, p.nt + 1)])
+            E_int = np.float64(0.0)
+            for k in range(1, p.nt + 1):
+                E_int += Et[k] * Et[k].conjugate() * (p.t_step * 1e15)
+            F = _F_value(p.F_type, gc[b], p.nb)
+            hl = p.h_lambda if p.task_type == "optimal_control_krotov" else np.float64(0.0)
+            J = F.real - hl * hl * E_int.real
+            self.goal_close_scal[b] += gc[b].sum()
+            E_list = np.array([abs(e) if e.imag else e.real for e in Et])
+            rows.append(IterRow(it, float(abs(self.goal_close_scal[b])), float(F.real), float(E_int.real), float(J), E_list))
+        return rows, gc
+
+    def run_prescribed(self):
+        """single_pot / filtering / trans_wo_control / intuitive_control (fitter.py:425-438)."""
+        self.goal_close_scal = np.zeros(self.B, np.complex128)
+        self.propagate(FORWARD)
+        E0s = [self._prescribed_field(p, FORWARD)[0] for p in self.pbs]
+        rows, _ = self._finish_forward(0, E0s)
+        return [[r] for r in rows]
+
+    def run_krotov(self, iter_max=None):
+        """optimal_control_krotov for every run (fitter.py:441-489, 537-569).  All runs iterate in
+        lock step; a run that has converged keeps its rows and is simply not reported further."""
+        pl = self.plan
+        hist: List[List[IterRow]] = [[] for _ in self.pbs]
+        done = np.zeros(self.B, bool)
+        sqrt_hf_T = np.array([np.complex128(cmath.sqrt(p.laser_field_hf(np.float64(1.0), p.T, p.pcos, p.w_list)))
+                              for p in self.pbs])
+        it = 0
+        E_start = [self._prescribed_field(p, FORWARD)[0] for p in self.pbs]
+        while True:
+            self.goal_close_scal = np.zeros(self.B, np.complex128)
+            pl.snapshot_load(0)
+            pl.record_state(0, 0, 0)                      # psi_tlist[0] = psi_init (fitter.py:227-229)
+            if it == 0:
+                pl.set_E_base(self._pad([self._prescribed_field(p, FORWARD) for p in self.pbs]))
+                pl.sweep(0, eng.FIELD_PRESCRIBED, 1, self.nt_max, True, -1, 0)
+                E0s = E_start
+            else:
+                pl.sweep(0, eng.FIELD_KROTOV_FWD, 0, self.nt_max + 1, True, 1, 0)
+                E0s = None
+            if E0s is None:
+                E0s = pl.get_fields()[:, 0]
+            rows, gc = self._finish_forward(it, E0s)
+            self.last_gc = gc
+            stop_all = True
+            for b, p in enumerate(self.pbs):
+                if done[b]:
+                    continue
+                hist[b].append(rows[b])
+                reached = abs(rows[b].Fsm - p.F_goal) <= p.epsilon
+                limit = p.iter_max if iter_max is None else iter_max
+                if reached or (it >= limit and limit != -1):
+                    if not (reached and it == 0):
+                        pass
+                    done[b] = True
+                else:
+                    stop_all = False
+            # the reference always runs the backward sweep of an iteration it started, unless the goal
+            # was met in iteration 0 (fitter.py:472-476); results of that sweep only matter to the next one
+            if stop_all:
+                break
+            pl.krotov_terminal(1, sqrt_hf_T, 1)
+            pl.sweep(1, eng.FIELD_KROTOV_BWD, 1, self.nt_max, True, 0, 1)
+            it += 1
+        return hist
+
+
+class NLevelBatch(_BatchBase):
+    """N-level (np = 1) runs: unitary-transformation optimal control and prescribed fields."""
+
+    def _upload_static(self):
+        uwd = np.array([[float(p.U), float(p.W), float(p.delta)] for p in self.pbs])
+        self.plan.set_static(np.stack([p.v for p in self.pbs]), None, uwd, self.dx)
+
+    def _field_rows(self, direction, half_step=False):
+        rows = []
+        for p in self.pbs:
+            r = []
+            for t in step_times(p, direction):
+                th = t - (abs(p.t_step) / 2.0) if half_step else t
+                r.append(p.laser_field(p.E0, th, p.t0, p.sigma) * p.laser_field_hf(np.float64(1.0), th, p.pcos, p.w_list))
+            rows.append(r)
+        return rows
+
+    def run_prescribed(self):
+        """trans_wo_control on an N-level system, e.g. the pi-pulse test (functional_tests.py:1072-1164)."""
+        pl = self.plan
+        pl.set_control(1.0, self.nt.astype(np.float64))
+        rows = self._field_rows(FORWARD)
+        pl.set_E_base(self._pad(rows))
+        pl.snapshot_load(0)
+        pl.sweep(0, eng.FIELD_PRESCRIBED, 1, self.nt_max, True, -1, -1)
+        E = pl.get_fields()
+        gc = pl.goal_overlap(1)
+        out = []
+        for b, p in enumerate(self.pbs):
+            Et = np.array([rows[b][0]] + [E[b, l] for l in range(1, p.nt + 1)])
+            E_int = np.float64(0.0)
+            for k in range(1, p.nt + 1):
+                E_int += Et[k] * Et[k].conjugate() * (p.t_step * 1e15)
+            F = _F_value(p.F_type, gc[b], p.nb)
+            E_list = np.array([abs(e) if e.imag else e.real for e in Et])
+            out.append([IterRow(0, float(abs(gc[b].sum())), float(F.real), float(E_int.real), float(F.real), E_list)])
+        return out
+
+    def _initial_row(self, b):
+        """iteration -1 report (fitter.py:494-535)."""
+        p = self.pbs[b]
+        gc0 = np.zeros(p.nb, np.complex128)
+        sc = np.float64(0.0)
+        for v in range(p.nb):
+            for n in range(p.nlevs):
+                gc0[v] += np.vdot(p.psi0[v][n], p.psif[v][n]) * p.dx
+            sc += gc0[v]
+        F0 = _F_value(p.F_type, gc0, p.nb)
+        El = [(p.laser_field(p.E0, t, p.t0, p.sigma) * p.laser_field_hf(np.float64(1.0), t, p.pcos, p.w_list)).real
+              for t in p.t_list]
+        Ei = np.float64(0.0)
+        for k in range(len(El) - 1):
+            Ei += El[k + 1] * np.conjugate(El[k + 1]) * (p.t_step * 1e15)
+        h0 = p.h_lambda * RED_PLANCK_H / CM_TO_ERG if p.ntriv == -1 else p.h_lambda
+        return IterRow(-1, float(abs(sc)), float(F0.real), float(Ei), float(F0.real - h0 * h0 * Ei), np.array(El))
+
+    def run_unit_transform(self, iter_max=None):
+        """optimal_control_unit_transform for every run (fitter.py:441-569, 709-778, 799-807)."""
+        pl = self.plan
+        B = self.B
+        hist: List[List[IterRow]] = [[self._initial_row(b)] for b in range(B)]
+        self.errors = [""] * B
+        done = np.zeros(B, bool)
+        goal_close_abs = np.zeros(B)
+        F_mid_1 = np.zeros(B)
+        h_lambda = np.ones(B)
+        a0 = np.zeros((B, self.pbs[0].nb), np.complex128)
+        s_rows = []
+        base_rows = []
+        for p in self.pbs:
+            sr, br = [0.0], [p.laser_field(p.E0, np.float64(0.0), p.t0, p.sigma) *
+                             p.laser_field_hf(np.float64(1.0), np.float64(0.0), p.pcos, p.w_list)]
+            for t in step_times(p, FORWARD)[1:]:
+                th = t - (abs(p.t_step) / 2.0)
+                s = p.laser_field(p.E0, th, p.t0, p.sigma) / p.E0
+                sr.append(s)
+                br.append(s * p.E0 * p.laser_field_hf(np.float64(1.0), th, p.pcos, p.w_list))
+            s_rows.append(sr)
+            base_rows.append(br)
+        pl.set_s_env(self._pad(s_rows))
+        it = 0
+        while True:
+            # ---- backward sweep from the goal basis (fitter.py:241-249) ----------------------------
+            pl.snapshot_load(1)
+            pl.record_state(1, 0)
+            if it == 0:
+                pl.set_control(1.0, self.nt.astype(np.float64))
+                pl.set_E_base(self._pad(self._field_rows(BACKWARD)))
+                pl.sweep(1, eng.FIELD_PRESCRIBED, 1, self.nt_max, True, -1, 1)
+            else:
+                pl.sweep(1, eng.FIELD_PRESCRIBED, 1, self.nt_max, True, -1, 1, reversed_E=True)
+            chi_init = pl.get_state()
+            # ---- l == 0 of the forward sweep: h_lambda and a0 (fitter.py:712-737) -------------------
+            for b, p in enumerate(self.pbs):
+                h0 = p.h_lambda * RED_PLANCK_H / CM_TO_ERG if p.ntriv == -1 else p.h_lambda
+                if p.h_lambda_mode == "dynamical" and goal_close_abs[b]:
+                    h_lambda[b] = h0 * p.nb / math.sqrt(goal_close_abs[b])
+                else:
+                    h_lambda[b] = h0
+                a0[b] = _a_value(p.F_type, p.psi0, chi_init[b], p.dx)
+            pl.set_control(h_lambda, self.nt.astype(np.float64), a0)
+            if it == 0:
+                pl.set_E_base(self._pad(base_rows))
+            pl.snapshot_load(0)
+            pl.sweep(0, eng.FIELD_UT_FWD, 0, self.nt_max + 1, True, 1, -1, write_E_base=True)
+            E = pl.get_fields()
+            gc = pl.goal_overlap(1)
+            stop_all = True
+            for b, p in enumerate(self.pbs):
+                if done[b]:
+                    continue
+                Et = E[b, :p.nt + 1]
+                E_int = np.float64(0.0)
+                for k in range(1, p.nt + 1):
+                    E_int += Et[k] * Et[k].conjugate() * (p.t_step * 1e15)
+                F = _F_value(p.F_type, gc[b], p.nb)
+                J = F.real - h_lambda[b] * h_lambda[b] * E_int.real
+                goal_close_abs[b] = abs(gc[b].sum())
+                E_list = np.array([abs(e) if e.imag else e.real for e in Et])
+                hist[b].append(IterRow(it, float(goal_close_abs[b]), float(F.real), float(E_int.real), float(J), E_list))
+                if p.q and it >= 1:                       # divergence guard (fitter.py:550-560)
+                    if it == p.iter_mid_1:
+                        F_mid_1[b] = F.real
+                    elif it == p.iter_mid_2:
+                        lim = -p.nb * p.nb * p.q
+                        if F_mid_1[b] > lim or F.real > lim or F_mid_1[b] < F.real:
+                            self.errors[b] = "The calculation is probably going to diverge.  Stopping the run..."
+                            done[b] = True
+                            continue
+                limit = p.iter_max if iter_max is None else iter_max
+                if abs(F.real - p.F_goal) <= p.epsilon or (it >= limit and limit != -1):
+                    done[b] = True
+                else:
+                    stop_all = False
+            if stop_all:
+                break
+            it += 1
+        return hist

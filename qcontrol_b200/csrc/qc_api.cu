@@ -1,0 +1,815 @@
+// C ABI of qcontrol_b200 (see include/qcontrol_b200.h).  Host-side plumbing only:
+// device buffers, uploads, kernel launches.  The numerics live in qc_grid.cuh
+// (FFT grid, kernel A) and qc_nlevel.cuh (N-level systems, kernel B).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/qcontrol_b200.h"
+#include "qc_grid.cuh"
+#include "qc_nlevel.cuh"
+
+using qc::cd;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int32_t fail(int32_t code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define QC_CUDA(call)                                                                       \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess)                                                             \
+            return fail(QC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// objects
+// ---------------------------------------------------------------------------
+struct qc_context {
+    int device;
+    cudaStream_t stream;
+    bool owns_stream;
+    cudaEvent_t ev0, ev1;
+    long long launches;
+};
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (!count) return cudaSuccess;
+        return cudaMalloc(&p, count * sizeof(T));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+struct PolySlot {
+    DevBuf<double> xp, sc;
+    DevBuf<cd> dv;
+    int batched = 0;
+    bool set = false;
+};
+
+struct qc_plan {
+    qc_context *ctx;
+    qc_plan_desc d;
+    bool grid;
+    int log2n;
+    int nbp;                 // nb padded to a power of two (N-level thread groups)
+    long long nthreads;      // batch * nbp
+    size_t state_elems;      // batch*nb*nlevs*np
+    size_t traj_elems;
+    DevBuf<cd> psi, E_base, expL[2], s_env, E_out, a0, E_step, tw1, tw2, goal, gc, tmp_row;
+    DevBuf<cd> traj[2];
+    DevBuf<cd> snap[4];
+    DevBuf<double> v, kin, uwd, dx, ctl, norms;
+    int v_batched = 0, uwd_batched = 0, dx_batched = 0, expL_batched[2] = {0, 0}, s_batched = 0, ctl_batched = 0;
+    bool static_set = false, ctl_set = false;
+    PolySlot poly[2];
+};
+
+// ---------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------
+__global__ void broadcast_rows_kernel(cd *dst, const cd *src, long long row, long long rows) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < row * rows) dst[i] = src[i % row];
+}
+
+// gc[run][v] = sum_n dx * sum_x conj(psi[x]) * goal[x]      (cprod(goal, psi), math_base.py:21)
+__global__ void goal_overlap_kernel(const cd *psi, const cd *goal, long long goal_stride, const double *dx,
+                                    int dx_stride, int per_vec, cd *gc, int nb) {
+    const int item = blockIdx.x;          // run*nb + v
+    const int run = item / nb, v = item % nb;
+    const cd *a = psi + (long long)item * per_vec;
+    const cd *g = goal + goal_stride * run + (long long)v * per_vec;
+    double re = 0.0, im = 0.0;
+    for (int i = threadIdx.x; i < per_vec; i += blockDim.x) {
+        const cd p = a[i], q = g[i];
+        re += p.x * q.x + p.y * q.y;
+        im += p.x * q.y - p.y * q.x;
+    }
+    __shared__ double sr[32], si[32];
+    for (int o = 16; o > 0; o >>= 1) {
+        re += __shfl_xor_sync(0xffffffffu, re, o);
+        im += __shfl_xor_sync(0xffffffffu, im, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        sr[threadIdx.x >> 5] = re;
+        si[threadIdx.x >> 5] = im;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tr = 0.0, ti = 0.0;
+        for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) {
+            tr += sr[w];
+            ti += si[w];
+        }
+        const double h = dx[(long long)dx_stride * run];
+        gc[item] = qc::cmk(tr * h, ti * h);
+    }
+}
+
+// Krotov terminal condition, fitter.py:376-392 (grid plans, nb == 1, two levels)
+__global__ void krotov_terminal_kernel(cd *psi, const cd *goal, long long goal_stride, const cd *gc,
+                                       const cd *sqrt_hf, int hf_stride, const double *dx, int dx_stride,
+                                       cd *traj0, long long traj_run_stride, int np) {
+    const int run = blockIdx.x;
+    cd *st = psi + (long long)run * 2 * np;
+    const cd *gu = goal + goal_stride * run + np;        // goal level 1
+    const cd g = gc[run];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) {
+        const cd c = qc::cmul(g, gu[i]);
+        acc += c.x * c.x + c.y * c.y;
+    }
+    __shared__ double sr[32];
+    __shared__ double s_norm;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sr[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) t += sr[w];
+        s_norm = fabs(t * dx[(long long)dx_stride * run]);
+    }
+    __syncthreads();
+    const double nrm = s_norm;
+    const double s = nrm > 0.0 ? sqrt(nrm) : 1.0;
+    const cd hf = sqrt_hf[(long long)hf_stride * run];
+    cd *tr = traj0 ? traj0 + traj_run_stride * run : nullptr;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) {
+        cd c = qc::cmul(g, gu[i]);
+        c = qc::cmk(c.x / s, c.y / s);
+        st[i] = qc::cmk(0.0, 0.0);
+        st[np + i] = c;
+        if (tr) tr[i] = qc::cmul(c, hf);
+    }
+}
+
+// copy the current state into a trajectory slice
+__global__ void record_grid_kernel(const cd *psi, cd *traj, long long traj_run_stride, long long slice_off,
+                                   int level, int np) {
+    const int run = blockIdx.x;
+    const cd *src = psi + ((long long)run * 2 + level) * np;
+    cd *dst = traj + traj_run_stride * run + slice_off;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) dst[i] = src[i];
+}
+
+__global__ void record_nlevel_kernel(const cd *psi, cd *traj_slice, int nb, int nbp, int nl, long long nthreads) {
+    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gt >= nthreads) return;
+    const int run = (int)(gt / nbp), v = (int)(gt % nbp);
+    for (int n = 0; n < nl; ++n)
+        traj_slice[(long long)n * nthreads + gt] = v < nb ? psi[((long long)run * nb + v) * nl + n] : qc::cmk(0.0, 0.0);
+}
+
+__global__ void gather_nlevel_kernel(const cd *traj_slice, cd *out, int nb, int nbp, int nl, long long nthreads) {
+    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gt >= nthreads) return;
+    const int run = (int)(gt / nbp), v = (int)(gt % nbp);
+    if (v >= nb) return;
+    for (int n = 0; n < nl; ++n) out[((long long)run * nb + v) * nl + n] = traj_slice[(long long)n * nthreads + gt];
+}
+
+// FP64 FMA throughput: 8 independent chains per thread
+__global__ void fp64_peak_kernel(double *out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, c);
+            a1 = fma(a1, m, c);
+            a2 = fma(a2, m, c);
+            a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c);
+            a5 = fma(a5, m, c);
+            a6 = fma(a6, m, c);
+            a7 = fma(a7, m, c);
+        }
+    }
+    out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ---------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------
+static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+static int ilog2(int x) {
+    int r = 0;
+    while ((1 << r) < x) ++r;
+    return r;
+}
+
+static void fill_twiddles(int log2n, std::vector<cd> &t1, std::vector<cd> &t2) {
+    const int N = 1 << log2n, TPL = N / 16, R3 = N / 256;
+    const int S1 = TPL + (R3 < 8 ? R3 : 0);
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    t1.assign((size_t)16 * S1, qc::cmk(1.0, 0.0));
+    for (int k1 = 0; k1 < 16; ++k1)
+        for (int t = 0; t < TPL; ++t) {
+            const int m = (k1 * t) % N;
+            const long double ang = -two_pi * (long double)m / (long double)N;
+            t1[(size_t)k1 * S1 + t] = qc::cmk((double)cosl(ang), (double)sinl(ang));
+        }
+    const int M = 16 * R3;
+    t2.assign((size_t)16 * R3, qc::cmk(1.0, 0.0));
+    for (int k2 = 0; k2 < 16; ++k2)
+        for (int n3 = 0; n3 < R3; ++n3) {
+            const int m = (k2 * n3) % M;
+            const long double ang = -two_pi * (long double)m / (long double)M;
+            t2[(size_t)k2 * R3 + n3] = qc::cmk((double)cosl(ang), (double)sinl(ang));
+        }
+}
+
+template <typename T>
+static int32_t upload(qc_plan *pl, DevBuf<T> &buf, const void *host, size_t count) {
+    if (buf.n != count) QC_CUDA(buf.alloc(count));
+    QC_CUDA(cudaMemcpyAsync(buf.p, host, count * sizeof(T), cudaMemcpyHostToDevice, pl->ctx->stream));
+    QC_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+    return QC_OK;
+}
+
+// upload rows[ (batched ? batch : 1) ][row] into a buffer that is always [batch][row]
+static int32_t upload_rows_expanded(qc_plan *pl, DevBuf<cd> &buf, const double *host, int batched, size_t row) {
+    const size_t batch = pl->d.batch;
+    if (buf.n != batch * row) QC_CUDA(buf.alloc(batch * row));
+    cudaStream_t st = pl->ctx->stream;
+    if (batched) {
+        QC_CUDA(cudaMemcpyAsync(buf.p, host, batch * row * sizeof(cd), cudaMemcpyHostToDevice, st));
+    } else {
+        if (pl->tmp_row.n < row) QC_CUDA(pl->tmp_row.alloc(row));
+        QC_CUDA(cudaMemcpyAsync(pl->tmp_row.p, host, row * sizeof(cd), cudaMemcpyHostToDevice, st));
+        const long long total = (long long)batch * row;
+        broadcast_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(buf.p, pl->tmp_row.p, (long long)row,
+                                                                              (long long)batch);
+        pl->ctx->launches++;
+        QC_CUDA(cudaGetLastError());
+    }
+    QC_CUDA(cudaStreamSynchronize(st));
+    return QC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// library / context
+// ---------------------------------------------------------------------------
+extern "C" int32_t qc_abi_version(void) { return QC_ABI_VERSION; }
+extern "C" const char *qc_last_error(void) { return g_err.c_str(); }
+
+extern "C" int32_t qc_create(int32_t device, void *stream, qc_context **out) {
+    if (!out) return fail(QC_ERR_ARG, "qc_create: out is NULL");
+    int ndev = 0;
+    QC_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(QC_ERR_ARG, "qc_create: device %d of %d", device, ndev);
+    QC_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    QC_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(QC_ERR_ARG, "qc_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    qc_context *c = new qc_context();
+    c->device = device;
+    c->launches = 0;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+        c->owns_stream = false;
+    } else {
+        QC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->owns_stream = true;
+    }
+    QC_CUDA(cudaEventCreate(&c->ev0));
+    QC_CUDA(cudaEventCreate(&c->ev1));
+    *out = c;
+    return QC_OK;
+}
+
+extern "C" int32_t qc_destroy(qc_context *ctx) {
+    if (!ctx) return QC_OK;
+    cudaSetDevice(ctx->device);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return QC_OK;
+}
+
+extern "C" int32_t qc_synchronize(qc_context *ctx) {
+    if (!ctx) return fail(QC_ERR_ARG, "qc_synchronize: NULL context");
+    QC_CUDA(cudaSetDevice(ctx->device));
+    QC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return QC_OK;
+}
+
+extern "C" int32_t qc_timer_start(qc_context *ctx) {
+    if (!ctx) return fail(QC_ERR_ARG, "qc_timer_start: NULL context");
+    QC_CUDA(cudaSetDevice(ctx->device));
+    QC_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    return QC_OK;
+}
+
+extern "C" int32_t qc_timer_stop(qc_context *ctx, double *elapsed_ms) {
+    if (!ctx || !elapsed_ms) return fail(QC_ERR_ARG, "qc_timer_stop: NULL argument");
+    QC_CUDA(cudaSetDevice(ctx->device));
+    QC_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    QC_CUDA(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    QC_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    *elapsed_ms = ms;
+    return QC_OK;
+}
+
+extern "C" int64_t qc_launch_count(qc_context *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int32_t qc_measure_fp64_peak(qc_context *ctx, double *tflops) {
+    if (!ctx || !tflops) return fail(QC_ERR_ARG, "qc_measure_fp64_peak: NULL argument");
+    QC_CUDA(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    QC_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    double *out = nullptr;
+    QC_CUDA(cudaMalloc(&out, sizeof(double) * blocks * threads));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        QC_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(out, iters, 1.0 + rep);
+        ctx->launches++;
+        QC_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        QC_CUDA(cudaEventSynchronize(ctx->ev1));
+        float ms = 0.f;
+        QC_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaFree(out);
+    *tflops = best;
+    return QC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------
+extern "C" int32_t qc_plan_create(qc_context *ctx, const qc_plan_desc *desc, qc_plan **out) {
+    if (!ctx || !desc || !out) return fail(QC_ERR_ARG, "qc_plan_create: NULL argument");
+    const qc_plan_desc &d = *desc;
+    if (d.batch < 1 || d.nt_max < 1) return fail(QC_ERR_ARG, "qc_plan_create: batch=%d nt_max=%d", d.batch, d.nt_max);
+    if (!is_pow2(d.nch) || d.nch < 2 || d.nch > 128)
+        return fail(QC_ERR_ARG, "qc_plan_create: nch=%d must be a power of two in [2,128]", d.nch);
+    const bool grid = d.hamil == QC_HAMIL_NONTRIV;
+    if (grid) {
+        if (!is_pow2(d.np) || d.np < 256 || d.np > 2048)
+            return fail(QC_ERR_ARG, "qc_plan_create: grid plans need np in {256,512,1024,2048}, got %d", d.np);
+        if (d.nlevs != 2 || d.nb != 1)
+            return fail(QC_ERR_ARG, "qc_plan_create: the FFT-grid Hamiltonian has nlevs=2, nb=1 (task_manager.py:925-932)");
+    } else {
+        if (d.hamil < QC_HAMIL_TWO_LEVELS || d.hamil > QC_HAMIL_QUBIT)
+            return fail(QC_ERR_ARG, "qc_plan_create: unknown hamil %d", d.hamil);
+        if (d.np != 1) return fail(QC_ERR_ARG, "qc_plan_create: N-level plans need np=1 (newcheb.py:887-889), got %d", d.np);
+        if (d.nlevs < 2 || d.nlevs > 8) return fail(QC_ERR_ARG, "qc_plan_create: nlevs=%d outside [2,8]", d.nlevs);
+        if (d.hamil == QC_HAMIL_TWO_LEVELS && d.nlevs != 2) return fail(QC_ERR_ARG, "qc_plan_create: two_levels needs nlevs=2");
+        if (d.nb < 1 || d.nb > 32) return fail(QC_ERR_ARG, "qc_plan_create: nb=%d outside [1,32]", d.nb);
+        if (d.hf_hide) return fail(QC_ERR_ARG, "qc_plan_create: hf_hide is not defined for N-level systems (task_manager.py:916-917)");
+    }
+    QC_CUDA(cudaSetDevice(ctx->device));
+    qc_plan *pl = new qc_plan();
+    pl->ctx = ctx;
+    pl->d = d;
+    pl->grid = grid;
+    pl->log2n = grid ? ilog2(d.np) : 0;
+    pl->nbp = 1;
+    while (pl->nbp < d.nb) pl->nbp <<= 1;
+    pl->nthreads = (long long)d.batch * pl->nbp;
+    pl->state_elems = (size_t)d.batch * d.nb * d.nlevs * d.np;
+    const size_t nt1 = (size_t)d.nt_max + 1;
+    cudaError_t e = cudaSuccess;
+    auto chk = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    chk(pl->psi.alloc(pl->state_elems));
+    chk(pl->E_base.alloc((size_t)d.batch * nt1));
+    chk(pl->E_out.alloc((size_t)d.batch * nt1));
+    chk(pl->E_step.alloc(d.batch));
+    chk(pl->norms.alloc((size_t)d.batch * d.nb * d.nlevs));
+    chk(pl->gc.alloc((size_t)d.batch * d.nb));
+    chk(pl->a0.alloc((size_t)d.batch * d.nb));
+    if (d.store_traj) {
+        pl->traj_elems = grid ? (size_t)d.batch * nt1 * d.np : nt1 * (size_t)d.nlevs * (size_t)pl->nthreads;
+        chk(pl->traj[0].alloc(pl->traj_elems));
+        chk(pl->traj[1].alloc(pl->traj_elems));
+    }
+    if (e != cudaSuccess) {
+        const int32_t rc = fail(QC_ERR_NOMEM, "qc_plan_create: device allocation failed: %s", cudaGetErrorString(e));
+        qc_plan_destroy(pl);
+        cudaGetLastError();
+        return rc;
+    }
+    QC_CUDA(cudaMemsetAsync(pl->E_base.p, 0, pl->E_base.n * sizeof(cd), ctx->stream));
+    QC_CUDA(cudaMemsetAsync(pl->E_out.p, 0, pl->E_out.n * sizeof(cd), ctx->stream));
+    QC_CUDA(cudaMemsetAsync(pl->a0.p, 0, pl->a0.n * sizeof(cd), ctx->stream));
+    if (grid) {
+        std::vector<cd> t1, t2;
+        fill_twiddles(pl->log2n, t1, t2);
+        int32_t rc = upload(pl, pl->tw1, t1.data(), t1.size());
+        if (rc == QC_OK) rc = upload(pl, pl->tw2, t2.data(), t2.size());
+        if (rc != QC_OK) {
+            qc_plan_destroy(pl);
+            return rc;
+        }
+    }
+    // default control row: h_lambda = 1, nt = nt_max
+    const double ctl[4] = {1.0, (double)d.nt_max, 0.0, 0.0};
+    int32_t rc = upload(pl, pl->ctl, ctl, 4);
+    if (rc != QC_OK) {
+        qc_plan_destroy(pl);
+        return rc;
+    }
+    pl->ctl_batched = 0;
+    *out = pl;
+    return QC_OK;
+}
+
+extern "C" int32_t qc_plan_destroy(qc_plan *pl) {
+    if (!pl) return QC_OK;
+    cudaSetDevice(pl->ctx->device);
+    cudaStreamSynchronize(pl->ctx->stream);
+    pl->psi.release(); pl->E_base.release(); pl->expL[0].release(); pl->expL[1].release(); pl->s_env.release(); pl->E_out.release();
+    pl->a0.release(); pl->E_step.release(); pl->tw1.release(); pl->tw2.release(); pl->goal.release();
+    pl->gc.release(); pl->tmp_row.release(); for (auto &b : pl->snap) b.release(); pl->traj[0].release(); pl->traj[1].release();
+    pl->v.release(); pl->kin.release(); pl->uwd.release(); pl->dx.release(); pl->ctl.release(); pl->norms.release();
+    for (auto &s : pl->poly) { s.xp.release(); s.sc.release(); s.dv.release(); }
+    delete pl;
+    return QC_OK;
+}
+
+extern "C" int32_t qc_set_static(qc_plan *pl, const double *v, int32_t v_batched, const double *akx2_re,
+                                 const double *uwd, int32_t uwd_batched, const double *dx, int32_t dx_batched) {
+    if (!pl || !v || !dx) return fail(QC_ERR_ARG, "qc_set_static: NULL argument");
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    const qc_plan_desc &d = pl->d;
+    int32_t rc = upload(pl, pl->v, v, (size_t)(v_batched ? d.batch : 1) * d.nlevs * d.np);
+    if (rc) return rc;
+    pl->v_batched = v_batched ? 1 : 0;
+    if (pl->grid) {
+        if (!akx2_re) return fail(QC_ERR_ARG, "qc_set_static: akx2_re is required for grid plans");
+        if ((rc = upload(pl, pl->kin, akx2_re, d.np))) return rc;
+    } else if (d.hamil != QC_HAMIL_TWO_LEVELS) {
+        if (!uwd) return fail(QC_ERR_ARG, "qc_set_static: (U, W, delta) required for BH_X/BH_Z/QUBIT");
+    }
+    if (uwd) {
+        if ((rc = upload(pl, pl->uwd, uwd, (size_t)(uwd_batched ? d.batch : 1) * 3))) return rc;
+        pl->uwd_batched = uwd_batched ? 1 : 0;
+    }
+    if ((rc = upload(pl, pl->dx, dx, dx_batched ? d.batch : 1))) return rc;
+    pl->dx_batched = dx_batched ? 1 : 0;
+    pl->static_set = true;
+    return QC_OK;
+}
+
+extern "C" int32_t qc_set_poly(qc_plan *pl, int32_t slot, const double *xp, const double *dv, const double *sc,
+                               int32_t batched) {
+    if (!pl || !xp || !dv || !sc) return fail(QC_ERR_ARG, "qc_set_poly: NULL argument");
+    if (slot < 0 || slot > 1) return fail(QC_ERR_ARG, "qc_set_poly: slot %d", slot);
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    const size_t rows = batched ? pl->d.batch : 1;
+    for (size_t r = 0; r < rows; ++r)
+        if (!(sc[r * 4 + 1] > sc[r * 4 + 0]))
+            return fail(QC_ERR_ARG, "qc_set_poly: emax (%g) must exceed emin (%g) in row %zu", sc[r * 4 + 1], sc[r * 4], r);
+    PolySlot &s = pl->poly[slot];
+    int32_t rc = upload(pl, s.xp, xp, pl->d.nch);
+    if (!rc) rc = upload(pl, s.dv, dv, rows * pl->d.nch);
+    if (!rc) rc = upload(pl, s.sc, sc, rows * 4);
+    if (rc) return rc;
+    s.batched = batched ? 1 : 0;
+    s.set = true;
+    return QC_OK;
+}
+
+extern "C" int32_t qc_set_state(qc_plan *pl, const double *psi) {
+    if (!pl || !psi) return fail(QC_ERR_ARG, "qc_set_state: NULL argument");
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    QC_CUDA(cudaMemcpyAsync(pl->psi.p, psi, pl->state_elems * sizeof(cd), cudaMemcpyHostToDevice, pl->ctx->stream));
+    QC_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+    return QC_OK;
+}
+
+extern "C" int32_t qc_get_state(qc_plan *pl, double *psi) {
+    if (!pl || !psi) return fail(QC_ERR_ARG, "qc_get_state: NULL argument");
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    QC_CUDA(cudaMemcpyAsync(psi, pl->psi.p, pl->state_elems * sizeof(cd), cudaMemcpyDeviceToHost, pl->ctx->stream));
+    QC_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+    return QC_OK;
+}
+
+extern "C" int32_t qc_set_step_scalars(qc_plan *pl, int32_t which, const double *vals, int32_t batched) {
+    if (!pl || !vals) return fail(QC_ERR_ARG, "qc_set_step_scalars: NULL argument");
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    const size_t row = (size_t)pl->d.nt_max + 1;
+    if (which == 0) return upload_rows_expanded(pl, pl->E_base, vals, batched, row);
+    if (which == 1 || which == 3) {
+        const int slot = which == 1 ? 0 : 1;
+        pl->expL_batched[slot] = batched ? 1 : 0;
+        return upload(pl, pl->expL[slot], vals, (batched ? pl->d.batch : 1) * row);
+    }
+    if (which == 2) {
+        pl->s_batched = batched ? 1 : 0;
+        return upload(pl, pl->s_env, vals, (batched ? pl->d.batch : 1) * row);
+    }
+    return fail(QC_ERR_ARG, "qc_set_step_scalars: which=%d", which);
+}
+
+extern "C" int32_t qc_set_control(qc_plan *pl, const double *ctl, int32_t batched, const double *a0) {
+    if (!pl || !ctl) return fail(QC_ERR_ARG, "qc_set_control: NULL argument");
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    const size_t rows = batched ? pl->d.batch : 1;
+    for (size_t r = 0; r < rows; ++r) {
+        const double nt = ctl[r * 4 + 1];
+        if (!(nt >= 1.0) || nt > pl->d.nt_max)
+            return fail(QC_ERR_ARG, "qc_set_control: nt=%g of row %zu outside [1, nt_max=%d]", nt, r, pl->d.nt_max);
+        if (ctl[r * 4 + 0] == 0.0) return fail(QC_ERR_ARG, "qc_set_control: h_lambda of row %zu is zero", r);
+    }
+    int32_t rc = upload(pl, pl->ctl, ctl, rows * 4);
+    if (rc) return rc;
+    pl->ctl_batched = batched ? 1 : 0;
+    if (a0) {
+        QC_CUDA(cudaMemcpyAsync(pl->a0.p, a0, pl->a0.n * sizeof(cd), cudaMemcpyHostToDevice, pl->ctx->stream));
+        QC_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+    }
+    return QC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// sweeps
+// ---------------------------------------------------------------------------
+template <int LOG2N>
+static int32_t launch_grid(qc_plan *pl, const qc::GridParams &gp) {
+    typedef qc::GridCfg<LOG2N> C;
+    static bool attr_done[64] = {false};
+    const int dev = pl->ctx->device;
+    if (!attr_done[dev & 63]) {
+        QC_CUDA(cudaFuncSetAttribute(qc::grid_sweep_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)C::SMEM_BYTES));
+        attr_done[dev & 63] = true;
+    }
+    qc::grid_sweep_kernel<LOG2N><<<gp.batch, C::NTHREADS, C::SMEM_BYTES, pl->ctx->stream>>>(gp);
+    pl->ctx->launches++;
+    QC_CUDA(cudaGetLastError());
+    return QC_OK;
+}
+
+template <int NL>
+static int32_t launch_nlevel(qc_plan *pl, const qc::NLevelParams &np_) {
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((np_.nthreads + threads - 1) / threads);
+    qc::nlevel_sweep_kernel<NL><<<blocks, threads, 0, pl->ctx->stream>>>(np_);
+    pl->ctx->launches++;
+    QC_CUDA(cudaGetLastError());
+    return QC_OK;
+}
+
+static int32_t run_sweep(qc_plan *pl, const qc_sweep_args *a, bool single_step) {
+    if (!pl || !a) return fail(QC_ERR_ARG, "qc_sweep: NULL argument");
+    const qc_plan_desc &d = pl->d;
+    if (!pl->static_set) return fail(QC_ERR_STATE, "qc_sweep: qc_set_static has not been called");
+    if (a->poly_slot < 0 || a->poly_slot > 1 || !pl->poly[a->poly_slot].set)
+        return fail(QC_ERR_STATE, "qc_sweep: polynomial slot %d has not been set", a->poly_slot);
+    if (a->nsteps < 1 || a->l_first < 0 || a->l_first > d.nt_max)
+        return fail(QC_ERR_ARG, "qc_sweep: l_first=%d nsteps=%d (nt_max=%d)", a->l_first, a->nsteps, d.nt_max);
+    const int mode = a->field_mode;
+    if (mode < 0 || mode > 3) return fail(QC_ERR_ARG, "qc_sweep: field_mode %d", mode);
+    if (pl->grid && mode == QC_FIELD_UT_FWD) return fail(QC_ERR_ARG, "qc_sweep: UT field update needs an N-level plan (newcheb.py:887-889)");
+    if (!pl->grid && (mode == QC_FIELD_KROTOV_FWD || mode == QC_FIELD_KROTOV_BWD))
+        return fail(QC_ERR_ARG, "qc_sweep: Krotov field update needs a grid plan");
+    if (a->traj_read > 1 || a->traj_write > 1 || (a->traj_read >= 0 && a->traj_read == a->traj_write))
+        return fail(QC_ERR_ARG, "qc_sweep: traj_read=%d traj_write=%d", a->traj_read, a->traj_write);
+    if ((a->traj_read >= 0 || a->traj_write >= 0) && !d.store_traj)
+        return fail(QC_ERR_STATE, "qc_sweep: plan was created without trajectory buffers");
+    if (mode != QC_FIELD_PRESCRIBED && a->traj_read < 0)
+        return fail(QC_ERR_ARG, "qc_sweep: field mode %d reads the previous sweep; traj_read must be 0 or 1", mode);
+    if (d.hf_hide && !single_step && !pl->expL[a->poly_slot < 0 || a->poly_slot > 1 ? 0 : a->poly_slot].p) return fail(QC_ERR_STATE, "qc_sweep: exp_L table (qc_set_step_scalars which=1) missing");
+    if (mode == QC_FIELD_UT_FWD && !pl->s_env.p) return fail(QC_ERR_STATE, "qc_sweep: s_env table (qc_set_step_scalars which=2) missing");
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    const PolySlot &ps = pl->poly[a->poly_slot];
+    if (pl->grid) {
+        qc::GridParams g;
+        memset(&g, 0, sizeof g);
+        g.batch = d.batch; g.nch = d.nch; g.nt_max = d.nt_max;
+        g.hf_hide = single_step ? 0 : d.hf_hide; g.renorm = a->renorm; g.field_mode = mode;
+        g.reversed_E = a->reversed_E; g.write_E_base = a->write_E_base;
+        g.l_first = a->l_first; g.nsteps = a->nsteps; g.single_step = single_step ? 1 : 0;
+        g.psi = pl->psi.p; g.v = pl->v.p; g.v_stride = pl->v_batched ? 2LL * d.np : 0; g.kin = pl->kin.p;
+        g.tw1 = pl->tw1.p; g.tw2 = pl->tw2.p; g.xp = ps.xp.p; g.dv = ps.dv.p; g.sc = ps.sc.p;
+        g.poly_stride = ps.batched; g.dx = pl->dx.p; g.dx_stride = pl->dx_batched;
+        g.E_base = pl->E_base.p; g.E_stride = 1; g.expL = pl->expL[a->poly_slot].p; g.expL_stride = pl->expL_batched[a->poly_slot];
+        g.ctl = pl->ctl.p; g.ctl_stride = pl->ctl_batched; g.E_step = pl->E_step.p; g.E_out = pl->E_out.p;
+        g.traj_in = a->traj_read >= 0 ? pl->traj[a->traj_read].p : nullptr;
+        g.traj_out = a->traj_write >= 0 ? pl->traj[a->traj_write].p : nullptr;
+        g.norms = pl->norms.p;
+        switch (pl->log2n) {
+            case 8: return launch_grid<8>(pl, g);
+            case 9: return launch_grid<9>(pl, g);
+            case 10: return launch_grid<10>(pl, g);
+            case 11: return launch_grid<11>(pl, g);
+        }
+        return fail(QC_ERR_ARG, "qc_sweep: unsupported np");
+    }
+    qc::NLevelParams n;
+    memset(&n, 0, sizeof n);
+    n.batch = d.batch; n.nb = d.nb; n.nbp = pl->nbp; n.nch = d.nch; n.nt_max = d.nt_max; n.hamil = d.hamil;
+    n.renorm = a->renorm; n.field_mode = mode; n.reversed_E = a->reversed_E; n.write_E_base = a->write_E_base;
+    n.l_first = a->l_first; n.nsteps = a->nsteps; n.single_step = single_step ? 1 : 0; n.nthreads = pl->nthreads;
+    n.psi = pl->psi.p; n.vdiag = pl->v.p; n.v_stride = pl->v_batched; n.uwd = pl->uwd.p; n.uwd_stride = pl->uwd_batched;
+    n.xp = ps.xp.p; n.dv = ps.dv.p; n.sc = ps.sc.p; n.poly_stride = ps.batched; n.dx = pl->dx.p; n.dx_stride = pl->dx_batched;
+    n.E_base = pl->E_base.p; n.E_stride = 1; n.s_env = pl->s_env.p; n.s_stride = pl->s_batched;
+    n.ctl = pl->ctl.p; n.ctl_stride = pl->ctl_batched; n.a0 = pl->a0.p; n.E_step = pl->E_step.p; n.E_out = pl->E_out.p;
+    n.traj_in = a->traj_read >= 0 ? pl->traj[a->traj_read].p : nullptr;
+    n.traj_out = a->traj_write >= 0 ? pl->traj[a->traj_write].p : nullptr;
+    n.norms = pl->norms.p;
+    switch (d.nlevs) {
+        case 2: return launch_nlevel<2>(pl, n);
+        case 3: return launch_nlevel<3>(pl, n);
+        case 4: return launch_nlevel<4>(pl, n);
+        case 5: return launch_nlevel<5>(pl, n);
+        case 6: return launch_nlevel<6>(pl, n);
+        case 7: return launch_nlevel<7>(pl, n);
+        case 8: return launch_nlevel<8>(pl, n);
+    }
+    return fail(QC_ERR_ARG, "qc_sweep: unsupported nlevs");
+}
+
+extern "C" int32_t qc_sweep(qc_plan *pl, const qc_sweep_args *a) { return run_sweep(pl, a, false); }
+
+extern "C" int32_t qc_prop_step(qc_plan *pl, int32_t poly_slot, const double *E) {
+    if (!pl || !E) return fail(QC_ERR_ARG, "qc_prop_step: NULL argument");
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    QC_CUDA(cudaMemcpyAsync(pl->E_step.p, E, pl->d.batch * sizeof(cd), cudaMemcpyHostToDevice, pl->ctx->stream));
+    qc_sweep_args a;
+    memset(&a, 0, sizeof a);
+    a.poly_slot = poly_slot; a.field_mode = QC_FIELD_PRESCRIBED; a.l_first = 1; a.nsteps = 1; a.renorm = 0;
+    a.traj_read = -1; a.traj_write = -1;
+    int32_t rc = run_sweep(pl, &a, true);
+    if (rc) return rc;
+    QC_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+    return QC_OK;
+}
+
+extern "C" int32_t qc_get_fields(qc_plan *pl, double *E_out) {
+    if (!pl || !E_out) return fail(QC_ERR_ARG, "qc_get_fields: NULL argument");
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    QC_CUDA(cudaMemcpyAsync(E_out, pl->E_out.p, pl->E_out.n * sizeof(cd), cudaMemcpyDeviceToHost, pl->ctx->stream));
+    QC_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+    return QC_OK;
+}
+
+extern "C" int32_t qc_get_norms(qc_plan *pl, double *norms) {
+    if (!pl || !norms) return fail(QC_ERR_ARG, "qc_get_norms: NULL argument");
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    QC_CUDA(cudaMemcpyAsync(norms, pl->norms.p, pl->norms.n * sizeof(double), cudaMemcpyDeviceToHost, pl->ctx->stream));
+    QC_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+    return QC_OK;
+}
+
+extern "C" int32_t qc_snapshot_set(qc_plan *pl, int32_t slot, const double *psi_host) {
+    if (!pl || slot < 0 || slot > 3) return fail(QC_ERR_ARG, "qc_snapshot_set: slot=%d", slot);
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    if (pl->snap[slot].n != pl->state_elems) QC_CUDA(pl->snap[slot].alloc(pl->state_elems));
+    if (psi_host) {
+        QC_CUDA(cudaMemcpyAsync(pl->snap[slot].p, psi_host, pl->state_elems * sizeof(cd), cudaMemcpyHostToDevice,
+                                pl->ctx->stream));
+        QC_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+    } else {
+        QC_CUDA(cudaMemcpyAsync(pl->snap[slot].p, pl->psi.p, pl->state_elems * sizeof(cd), cudaMemcpyDeviceToDevice,
+                                pl->ctx->stream));
+    }
+    return QC_OK;
+}
+
+extern "C" int32_t qc_snapshot_load(qc_plan *pl, int32_t slot) {
+    if (!pl || slot < 0 || slot > 3 || !pl->snap[slot].p) return fail(QC_ERR_ARG, "qc_snapshot_load: slot=%d is empty", slot);
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    QC_CUDA(cudaMemcpyAsync(pl->psi.p, pl->snap[slot].p, pl->state_elems * sizeof(cd), cudaMemcpyDeviceToDevice,
+                            pl->ctx->stream));
+    return QC_OK;
+}
+
+extern "C" int32_t qc_goal_overlap(qc_plan *pl, int32_t goal_slot, double *gc) {
+    if (!pl || goal_slot < 0 || goal_slot > 3 || !pl->snap[goal_slot].p)
+        return fail(QC_ERR_ARG, "qc_goal_overlap: snapshot slot %d is empty", goal_slot);
+    if (!pl->dx.p) return fail(QC_ERR_STATE, "qc_goal_overlap: qc_set_static has not been called");
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    const qc_plan_desc &d = pl->d;
+    const int per_vec = d.nlevs * d.np;
+    goal_overlap_kernel<<<d.batch * d.nb, per_vec >= 256 ? 256 : 32, 0, pl->ctx->stream>>>(
+        pl->psi.p, pl->snap[goal_slot].p, (long long)d.nb * per_vec, pl->dx.p, pl->dx_batched, per_vec, pl->gc.p, d.nb);
+    pl->ctx->launches++;
+    QC_CUDA(cudaGetLastError());
+    if (gc) {
+        QC_CUDA(cudaMemcpyAsync(gc, pl->gc.p, pl->gc.n * sizeof(cd), cudaMemcpyDeviceToHost, pl->ctx->stream));
+        QC_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+    }
+    return QC_OK;
+}
+
+extern "C" int32_t qc_krotov_terminal(qc_plan *pl, int32_t goal_slot, const double *gc, const double *sqrt_hf_T,
+                                      int32_t hf_batched, int32_t traj_write) {
+    if (!pl || !sqrt_hf_T) return fail(QC_ERR_ARG, "qc_krotov_terminal: NULL argument");
+    if (!pl->grid) return fail(QC_ERR_ARG, "qc_krotov_terminal: grid plans only (task_manager.py:925-932)");
+    if (goal_slot < 0 || goal_slot > 3 || !pl->snap[goal_slot].p)
+        return fail(QC_ERR_ARG, "qc_krotov_terminal: snapshot slot %d is empty", goal_slot);
+    if (traj_write > 1 || (traj_write >= 0 && !pl->d.store_traj)) return fail(QC_ERR_ARG, "qc_krotov_terminal: traj_write=%d", traj_write);
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    const qc_plan_desc &d = pl->d;
+    if (gc) QC_CUDA(cudaMemcpyAsync(pl->gc.p, gc, pl->gc.n * sizeof(cd), cudaMemcpyHostToDevice, pl->ctx->stream));
+    const size_t hrows = hf_batched ? d.batch : 1;
+    if (pl->tmp_row.n < hrows) QC_CUDA(pl->tmp_row.alloc(hrows));
+    QC_CUDA(cudaMemcpyAsync(pl->tmp_row.p, sqrt_hf_T, hrows * sizeof(cd), cudaMemcpyHostToDevice, pl->ctx->stream));
+    krotov_terminal_kernel<<<d.batch, 256, 0, pl->ctx->stream>>>(
+        pl->psi.p, pl->snap[goal_slot].p, 2LL * d.np, pl->gc.p, pl->tmp_row.p, hf_batched ? 1 : 0, pl->dx.p,
+        pl->dx_batched, traj_write >= 0 ? pl->traj[traj_write].p : nullptr, (long long)(d.nt_max + 1) * d.np, d.np);
+    pl->ctx->launches++;
+    QC_CUDA(cudaGetLastError());
+    QC_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+    return QC_OK;
+}
+
+extern "C" int32_t qc_get_traj(qc_plan *pl, int32_t buffer, int32_t index, double *out) {
+    if (!pl || !out) return fail(QC_ERR_ARG, "qc_get_traj: NULL argument");
+    if (buffer < 0 || buffer > 1 || !pl->d.store_traj || index < 0 || index > pl->d.nt_max)
+        return fail(QC_ERR_ARG, "qc_get_traj: buffer=%d index=%d", buffer, index);
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    const qc_plan_desc &d = pl->d;
+    cudaStream_t st = pl->ctx->stream;
+    if (pl->grid) {
+        QC_CUDA(cudaMemcpy2DAsync(out, (size_t)d.np * sizeof(cd), pl->traj[buffer].p + (size_t)index * d.np,
+                                  (size_t)(d.nt_max + 1) * d.np * sizeof(cd), (size_t)d.np * sizeof(cd), d.batch,
+                                  cudaMemcpyDeviceToHost, st));
+    } else {
+        const size_t n = (size_t)d.batch * d.nb * d.nlevs;
+        if (pl->goal.n < n) QC_CUDA(pl->goal.alloc(n));
+        const cd *slice = pl->traj[buffer].p + (size_t)index * d.nlevs * pl->nthreads;
+        gather_nlevel_kernel<<<(unsigned)((pl->nthreads + 127) / 128), 128, 0, st>>>(slice, pl->goal.p, d.nb, pl->nbp,
+                                                                                   d.nlevs, pl->nthreads);
+        pl->ctx->launches++;
+        QC_CUDA(cudaGetLastError());
+        QC_CUDA(cudaMemcpyAsync(out, pl->goal.p, n * sizeof(cd), cudaMemcpyDeviceToHost, st));
+    }
+    QC_CUDA(cudaStreamSynchronize(st));
+    return QC_OK;
+}
+
+extern "C" int32_t qc_record_state(qc_plan *pl, int32_t buffer, int32_t index, int32_t level) {
+    if (!pl) return fail(QC_ERR_ARG, "qc_record_state: NULL plan");
+    if (buffer < 0 || buffer > 1 || !pl->d.store_traj || index < 0 || index > pl->d.nt_max)
+        return fail(QC_ERR_ARG, "qc_record_state: buffer=%d index=%d", buffer, index);
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    const qc_plan_desc &d = pl->d;
+    if (pl->grid) {
+        if (level < 0 || level > 1) return fail(QC_ERR_ARG, "qc_record_state: level=%d", level);
+        record_grid_kernel<<<d.batch, 256, 0, pl->ctx->stream>>>(pl->psi.p, pl->traj[buffer].p,
+                                                                (long long)(d.nt_max + 1) * d.np,
+                                                                (long long)index * d.np, level, d.np);
+    } else {
+        cd *slice = pl->traj[buffer].p + (size_t)index * d.nlevs * pl->nthreads;
+        record_nlevel_kernel<<<(unsigned)((pl->nthreads + 127) / 128), 128, 0, pl->ctx->stream>>>(
+            pl->psi.p, slice, d.nb, pl->nbp, d.nlevs, pl->nthreads);
+    }
+    pl->ctx->launches++;
+    QC_CUDA(cudaGetLastError());
+    return QC_OK;
+}
+
+extern "C" int32_t qc_propagate_host(qc_plan *pl, const qc_sweep_args *args, const double *psi_in, double *psi_out) {
+    if (!pl || !args || !psi_in || !psi_out) return fail(QC_ERR_ARG, "qc_propagate_host: NULL argument");
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    cudaStream_t st = pl->ctx->stream;
+    QC_CUDA(cudaMemcpyAsync(pl->psi.p, psi_in, pl->state_elems * sizeof(cd), cudaMemcpyHostToDevice, st));
+    int32_t rc = run_sweep(pl, args, false);
+    if (rc) return rc;
+    QC_CUDA(cudaMemcpyAsync(psi_out, pl->psi.p, pl->state_elems * sizeof(cd), cudaMemcpyDeviceToHost, st));
+    QC_CUDA(cudaStreamSynchronize(st));
+    return QC_OK;
+}

@@ -1,0 +1,338 @@
+// Kernel A: fused Newton-polynomial time stepper for the two-level FFT-grid
+// Hamiltonian (Hamil2DNonTrivial, hamil_2d.py:34-73).
+//
+// One CTA owns one run (one two-level wavefunction) for a whole launch of
+// `nsteps` time steps.  2*TPL threads, TPL = N/16: thread (level, t) keeps the 16
+// grid points x = t + TPL*n1 of its level in registers, for both the recurrence
+// vector phi and the accumulator psi.  Per polynomial order the only data that
+// leaves the register file are the four FFT transposes and the phi stash, all in
+// shared memory; HBM is touched once per time step (trajectory slice in/out).
+//
+// FFT: N = 16*16*R3 (R3 = N/256), decimation in frequency forward, the exact
+// mirror inverse, so no reordering pass is needed and the k-space multiply runs
+// on the permuted layout with a per-thread register copy of the multiplier.
+#pragma once
+#include "qc_fft.cuh"
+
+namespace qc {
+
+struct GridParams {
+    int batch, nch, nt_max;
+    int hf_hide, renorm, field_mode, reversed_E, write_E_base;
+    int l_first, nsteps;
+    int single_step;             // 1: qc_prop_step semantics (explicit E, no transform / renorm)
+    cd *psi;                     // [batch][2][N]
+    const double *v;             // [vb][2][N]
+    long long v_stride;
+    const double *kin;           // [N]
+    const cd *tw1;               // [16][S1]
+    const cd *tw2;               // [16][R3]
+    const double *xp;            // [nch]
+    const cd *dv;                // [pb][nch]
+    const double *sc;            // [pb][4] emin emax t_sc eL
+    int poly_stride;             // 0 or 1 (in runs)
+    const double *dx;            // [db]
+    int dx_stride;
+    cd *E_base;                  // [eb][nt_max+1]
+    int E_stride;                // 0 or 1 (in runs)
+    const cd *expL;              // [xb][nt_max+1]
+    int expL_stride;
+    const double *ctl;           // [cb][4] h_lambda, nt
+    int ctl_stride;
+    const cd *E_step;            // [batch] explicit field for single_step
+    cd *E_out;                   // [batch][nt_max+1]
+    const cd *traj_in;           // [batch][nt_max+1][N]  or null
+    cd *traj_out;                // [batch][nt_max+1][N]  or null
+    double *norms;               // [batch][2]
+};
+
+template <int LOG2N>
+struct GridCfg {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int TPL = N / 16;          // threads per level
+    static constexpr int R3 = N / 256;          // third radix (1,2,4,8)
+    static constexpr int Q = 16 / R3;           // R3-point DFTs per thread in pass 3
+    static constexpr int S1 = TPL + (R3 < 8 ? R3 : 0);   // padded row stride of the transpose buffers
+    static constexpr int BUF = 16 * S1;         // complex elements per transpose buffer
+    static constexpr int NTHREADS = 2 * TPL;
+    // shared memory (in complex elements): per level A, B, S ; tables tw1, tw2 ; then doubles
+    static constexpr size_t SMEM_BYTES =
+        sizeof(cd) * (size_t)(2 * (2 * BUF + N) + BUF + 16 * R3) + sizeof(double) * (size_t)(3 * 128 + 64);
+};
+
+// skewed position of element (k2, n3) inside a lane group's private 16*R3 region
+template <int R3, int Q>
+__device__ __forceinline__ int pos2(int k2, int n3) {
+    return k2 * R3 + ((n3 + k2 / Q) & (R3 - 1));
+}
+
+// Sum `val` over the threads of each level; every thread gets both sums.
+template <int NTHREADS, int TPL>
+__device__ __forceinline__ void level_sums(double val, double *s_red, int tid, double &sum0, double &sum1) {
+    constexpr int G = TPL < 32 ? TPL : 32;        // lanes that share a level inside a warp
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+    if ((tid & (G - 1)) == 0) s_red[tid / G] = val;
+    __syncthreads();
+    constexpr int NG = NTHREADS / G;
+    sum0 = 0.0;
+    sum1 = 0.0;
+#pragma unroll
+    for (int g = 0; g < NG / 2; ++g) sum0 += s_red[g];
+#pragma unroll
+    for (int g = NG / 2; g < NG; ++g) sum1 += s_red[g];
+    __syncthreads();
+}
+
+template <int LOG2N>
+__global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel(GridParams p) {
+    typedef GridCfg<LOG2N> C;
+    constexpr int N = C::N, TPL = C::TPL, R3 = C::R3, Q = C::Q, S1 = C::S1, BUF = C::BUF;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cd *sm = reinterpret_cast<cd *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int lev = tid / TPL;
+    const int t = tid - lev * TPL;
+    cd *bufA = sm + lev * (2 * BUF + N);
+    cd *bufB = bufA + BUF;
+    cd *stash = bufB + BUF;
+    const cd *stash_other = sm + (1 - lev) * (2 * BUF + N) + 2 * BUF;
+    cd *tw1 = sm + 2 * (2 * BUF + N);
+    cd *tw2 = tw1 + BUF;
+    double *s_xp = reinterpret_cast<double *>(tw2 + 16 * R3);
+    cd *s_dv = reinterpret_cast<cd *>(s_xp + 128);
+    double *s_red = s_xp + 3 * 128;              // 64 doubles of reduction scratch
+
+    const int run = blockIdx.x;
+    if (run >= p.batch) return;
+    const int k1p = t / R3;       // k1' : which pass-1 output row this thread transforms in pass 2
+    const int n3p = t % R3;       // n3' (also the lane's index c inside its group in pass 3)
+
+    // ---- tables -------------------------------------------------------------
+    for (int i = tid; i < BUF; i += C::NTHREADS) tw1[i] = p.tw1[i];
+    for (int i = tid; i < 16 * R3; i += C::NTHREADS) tw2[i] = p.tw2[i];
+    const long long prun = (long long)p.poly_stride * run;
+    for (int i = tid; i < p.nch; i += C::NTHREADS) {
+        s_xp[i] = p.xp[i];
+        s_dv[i] = p.dv[prun * p.nch + i];
+    }
+    const double emin = p.sc[prun * 4 + 0], emax = p.sc[prun * 4 + 1], t_sc = p.sc[prun * 4 + 2],
+                 eL = p.sc[prun * 4 + 3];
+    const double c1 = 4.0 / (emax - emin);                       // phys_base.py:100
+    const double c2 = 2.0 * (emax + emin) / (emax - emin);       // phys_base.py:101
+    const double dx = p.dx[(long long)p.dx_stride * run];
+    const double h_lambda = p.ctl[(long long)p.ctl_stride * run * 4 + 0];
+    const int nt = (int)p.ctl[(long long)p.ctl_stride * run * 4 + 1];
+    double ph_s, ph_c;
+    sincos(-2.0 * t_sc * (emax + emin) / (emax - emin), &ph_s, &ph_c);   // phys_base.py:174
+    const cd phase = cmk(ph_c, ph_s);
+
+    // per-thread constants: diagonal d(x) = c1*(v(x) +- eL) - c2 and k-space multiplier
+    double dcoef[16], kc[16];
+    {
+        const double *vr = p.v + p.v_stride * run + (long long)lev * N;
+        const double sgn = lev == 0 ? eL : -eL;                  // hamil_2d.py:50-51, 66-67
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) dcoef[n1] = fma(c1, vr[t + TPL * n1] + sgn, -c2);
+        const double kscale = c1 / (double)N;                     // 1/N of numpy's ifft
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const int q = e / R3, k3 = e % R3;
+            const int k = k1p + 16 * (n3p * Q + q) + 256 * k3;
+            kc[e] = p.kin[k] * kscale;
+        }
+    }
+
+    cd psi[16], a[16];
+    {
+        const cd *src = p.psi + ((long long)run * 2 + lev) * N;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) psi[n1] = src[t + TPL * n1];
+    }
+    __syncthreads();
+
+    const cd *traj_in = p.traj_in ? p.traj_in + (long long)run * (p.nt_max + 1) * N : nullptr;
+    cd *traj_out = p.traj_out ? p.traj_out + (long long)run * (p.nt_max + 1) * N : nullptr;
+    const long long erun = (long long)p.E_stride * run * (p.nt_max + 1);
+    const long long xrun = (long long)p.expL_stride * run * (p.nt_max + 1);
+    cd *E_out = p.E_out + (long long)run * (p.nt_max + 1);
+    // which level records / reads trajectories: forward sweeps record level 0 and read the stored
+    // level 1 of chi; backward sweeps record level 1 and read level 0 of psi (fitter.py:700-706, 791-796)
+    const int ov_lev = p.field_mode == 2 ? 1 : 0;
+
+    for (int l = p.l_first; l < p.l_first + p.nsteps && l <= nt; ++l) {
+        const bool start_only = (l == 0);   // start(): only the initial field is evaluated (propagation.py:360-361)
+        // ---- rotating frame in (propagation.py:383-390) ---------------------
+        cd eLx = cmk(1.0, 0.0);
+        if (p.hf_hide && !start_only) {
+            eLx = p.expL[xrun + l];
+            const double den = eLx.x * eLx.x + eLx.y * eLx.y;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (lev == 0) {
+                    cd n = cmulc(psi[i], eLx);
+                    psi[i] = cmk(n.x / den, n.y / den);
+                } else {
+                    psi[i] = cmul(psi[i], eLx);
+                }
+            }
+        }
+        // ---- field of this step (fitter.py:650-811) --------------------------
+        double E;
+        if (p.single_step) {
+            E = p.E_step[run].x;
+        } else if (p.field_mode == 0) {
+            const int le = p.reversed_E ? (l == 0 ? nt : nt - l + 1) : l;
+            E = p.E_base[erun + le].x;
+        } else {
+            double part = 0.0;
+            if (lev == ov_lev) {
+                const cd *tr = traj_in + (long long)(nt - l) * N;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const cd c = tr[t + TPL * i];
+                    // forward: Im(conj(psi) * chi) ; backward: Im(conj(psi_old) * chi)
+                    part += p.field_mode == 1 ? (psi[i].x * c.y - psi[i].y * c.x) : (c.x * psi[i].y - c.y * psi[i].x);
+                }
+            }
+            double t0s, t1s;
+            level_sums<C::NTHREADS, TPL>(part, s_red, tid, t0s, t1s);
+            const double tot = t0s + t1s;
+            E = -2.0 * (tot * dx) / h_lambda;
+        }
+        if (tid == 0 && !p.single_step) {
+            E_out[l] = cmk(E, 0.0);
+            if (p.write_E_base) p.E_base[erun + l] = cmk(E, 0.0);
+        }
+        if (start_only) continue;
+        const double cE = c1 * E;
+
+        // ---- Newton recurrence (phys_base.py:158-172) ------------------------
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            a[i] = psi[i];
+            psi[i] = cmul(psi[i], s_dv[0]);
+        }
+        for (int j = 0; j < p.nch - 1; ++j) {
+            const double xpj = s_xp[j];
+            const cd dvj = s_dv[j + 1];
+            // stash phi (own slots, natural x order)
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) stash[t + TPL * n1] = a[n1];
+            // pass 1 : DFT over n1, twiddle w_N^(k1*t)
+            dft16<false>(a);
+#pragma unroll
+            for (int k1 = 1; k1 < 16; ++k1) a[k1] = cmul(a[k1], tw1[k1 * S1 + t]);
+#pragma unroll
+            for (int k1 = 0; k1 < 16; ++k1) bufA[k1 * S1 + t] = a[k1];
+            __syncthreads();                                                       // (#1)
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) a[n2] = bufA[k1p * S1 + n2 * R3 + n3p];
+            // pass 2 : DFT over n2, twiddle w_{16 R3}^(k2*n3)
+            dft16<false>(a);
+            if (R3 > 1) {
+#pragma unroll
+                for (int k2 = 1; k2 < 16; ++k2) a[k2] = cmul(a[k2], tw2[k2 * R3 + n3p]);
+                __syncwarp();
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2) bufA[k1p * S1 + pos2<R3, Q>(k2, n3p)] = a[k2];
+                __syncwarp();
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    a[e] = bufA[k1p * S1 + pos2<R3, Q>(n3p * Q + e / R3, e % R3)];
+                // pass 3 : Q DFTs of size R3 over n3 ; k-space multiply ; inverse pass 3
+#pragma unroll
+                for (int q = 0; q < Q; ++q) dft<R3, false>(a + q * R3);
+            }
+#pragma unroll
+            for (int e = 0; e < 16; ++e) a[e] = cscale(a[e], kc[e]);
+            if (R3 > 1) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q) dft<R3, true>(a + q * R3);
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    bufB[k1p * S1 + pos2<R3, Q>(n3p * Q + e / R3, e % R3)] = a[e];
+                __syncwarp();
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2) a[k2] = bufB[k1p * S1 + pos2<R3, Q>(k2, n3p)];
+#pragma unroll
+                for (int k2 = 1; k2 < 16; ++k2) a[k2] = cmulc(a[k2], tw2[k2 * R3 + n3p]);
+                __syncwarp();
+            }
+            // inverse pass 2
+            dft16<true>(a);
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) bufB[k1p * S1 + n2 * R3 + n3p] = a[n2];
+            __syncthreads();                                                       // (#2)
+#pragma unroll
+            for (int k1 = 0; k1 < 16; ++k1) a[k1] = bufB[k1 * S1 + t];
+#pragma unroll
+            for (int k1 = 1; k1 < 16; ++k1) a[k1] = cmulc(a[k1], tw1[k1 * S1 + t]);
+            // inverse pass 1 -> kinetic term (already scaled by c1) at x = t + TPL*n1
+            dft16<true>(a);
+            // pointwise part (hamil_2d.py:60-71, phys_base.py:98-111) and accumulation (phys_base.py:170-172)
+            const double shift = xpj;
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) {
+                const cd own = stash[t + TPL * n1];
+                const cd oth = stash_other[t + TPL * n1];
+                const double dd = dcoef[n1] - shift;
+                cd r;
+                r.x = fma(dd, own.x, fma(-cE, oth.x, a[n1].x));
+                r.y = fma(dd, own.y, fma(-cE, oth.y, a[n1].y));
+                a[n1] = r;
+                psi[n1] = cfma(dvj, r, psi[n1]);
+            }
+            __syncthreads();                                                       // (#3) stash reuse
+        }
+        // ---- final phase (phys_base.py:174-176), norms, renormalisation --------
+        double nrm = 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            psi[i] = cmul(psi[i], phase);
+            nrm = fma(psi[i].x, psi[i].x, fma(psi[i].y, psi[i].y, nrm));
+        }
+        if (!p.single_step) {
+            double n0, n1s;
+            level_sums<C::NTHREADS, TPL>(nrm, s_red, tid, n0, n1s);
+            n0 *= dx;
+            n1s *= dx;
+            if (tid == 0) {
+                p.norms[run * 2 + 0] = n0;
+                p.norms[run * 2 + 1] = n1s;
+            }
+            const double tot = fabs(n0 + n1s);
+            if (p.renorm && tot > 0.0) {                     // propagation.py:430-433
+                const double s = sqrt(tot);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) psi[i] = cmk(psi[i].x / s, psi[i].y / s);
+            }
+            // ---- record the rotating-frame state (fitter.py:301-309, 322-329) -----
+            if (traj_out && lev == (p.field_mode == 2 ? 1 : 0)) {
+                cd *dst = traj_out + (long long)l * N;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) dst[t + TPL * i] = psi[i];
+            }
+            // ---- rotating frame out (propagation.py:440-441) ---------------------
+            if (p.hf_hide) {
+                const double den = eLx.x * eLx.x + eLx.y * eLx.y;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if (lev == 0) {
+                        psi[i] = cmul(psi[i], eLx);
+                    } else {
+                        cd n = cmulc(psi[i], eLx);
+                        psi[i] = cmk(n.x / den, n.y / den);
+                    }
+                }
+            }
+        }
+    }
+    {
+        cd *dst = p.psi + ((long long)run * 2 + lev) * N;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) dst[t + TPL * n1] = psi[n1];
+    }
+}
+
+}  // namespace qc

@@ -1,0 +1,219 @@
+// Kernel B: N-level systems without a spatial grid (np == 1): the tridiagonal
+// angular-momentum / Bose-Hubbard Hamiltonians BH_X, BH_Z, the qubit and the
+// trivial two-level model (hamil_2d.py:76-187).
+//
+// One thread owns one basis vector of one run for a whole sweep: state, Newton
+// recurrence and renormalisation are register-only.  The nb basis vectors of a
+// run sit in adjacent lanes so the unitary-transformation field update
+// (fitter.py:739-778), which couples them at every step, is a few shuffles.
+// Trajectory slices are stored [slice][level][thread] so that a warp reads and
+// writes contiguous 512-byte rows.
+#pragma once
+#include "qc_fft.cuh"
+
+namespace qc {
+
+struct NLevelParams {
+    int batch, nb, nbp, nch, nt_max, hamil;
+    int renorm, field_mode, reversed_E, write_E_base;
+    int l_first, nsteps, single_step;
+    long long nthreads;          // batch * nbp
+    cd *psi;                     // [batch][nb][NL]
+    const double *vdiag;         // [vb][NL]  the constant arrays v[n][1] (two_levels only)
+    int v_stride;
+    const double *uwd;           // [ub][3]
+    int uwd_stride;
+    const double *xp;            // [nch]
+    const cd *dv;                // [pb][nch]
+    const double *sc;            // [pb][4]
+    int poly_stride;
+    const double *dx;
+    int dx_stride;
+    cd *E_base;                  // [eb][nt_max+1]
+    int E_stride;
+    const cd *s_env;             // [sb][nt_max+1]
+    int s_stride;
+    const double *ctl;           // [cb][4] h_lambda, nt
+    int ctl_stride;
+    const cd *a0;                // [batch][nb]
+    const cd *E_step;            // [batch]
+    cd *E_out;                   // [batch][nt_max+1]
+    const cd *traj_in;           // [nt_max+1][NL][nthreads]
+    cd *traj_out;
+    double *norms;               // [batch][nb][NL]
+};
+
+// phi_out = H(E) phi for the tridiagonal level matrix (diag real, off-diagonals complex)
+template <int NL>
+__device__ __forceinline__ void tri_apply(const double *dg, const cd *up, const cd *lo, const cd *in, cd *out) {
+#pragma unroll
+    for (int g = 0; g < NL; ++g) {
+        cd acc = cmk(0.0, 0.0);
+        if (g > 0) acc = cmul(lo[g], in[g - 1]);            // H[g, g-1]
+        acc = cadd(acc, cscale(in[g], dg[g]));              // H[g, g]
+        if (g < NL - 1) acc = cadd(acc, cmul(up[g + 1], in[g + 1]));  // H[g, g+1]
+        out[g] = acc;
+    }
+}
+
+template <int NL>
+__global__ void __launch_bounds__(128) nlevel_sweep_kernel(NLevelParams p) {
+    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = gt < p.nthreads;
+    const int run = in_range ? (int)(gt / p.nbp) : 0;
+    const int vec = in_range ? (int)(gt % p.nbp) : 0;
+    const bool active = in_range && vec < p.nb;
+
+    const long long prun = (long long)p.poly_stride * run;
+    const double emin = p.sc[prun * 4 + 0], emax = p.sc[prun * 4 + 1], t_sc = p.sc[prun * 4 + 2];
+    const double c1 = 4.0 / (emax - emin);
+    const double c2 = 2.0 * (emax + emin) / (emax - emin);
+    const double dx = p.dx[(long long)p.dx_stride * run];
+    const double h_lambda = p.ctl[(long long)p.ctl_stride * run * 4 + 0];
+    const int nt = (int)p.ctl[(long long)p.ctl_stride * run * 4 + 1];
+    const double U = p.uwd ? p.uwd[(long long)p.uwd_stride * run * 3 + 0] : 0.0;
+    const double W = p.uwd ? p.uwd[(long long)p.uwd_stride * run * 3 + 1] : 0.0;
+    const double delta = p.uwd ? p.uwd[(long long)p.uwd_stride * run * 3 + 2] : 0.0;
+    double ph_s, ph_c;
+    sincos(-2.0 * t_sc * (emax + emin) / (emax - emin), &ph_s, &ph_c);
+    const cd phase = cmk(ph_c, ph_s);
+    const cd *dv = p.dv + prun * p.nch;
+    const cd a0 = (p.a0 && active) ? p.a0[(long long)run * p.nb + vec] : cmk(0.0, 0.0);
+
+    // E-independent parts of the level matrix
+    const double lq = (NL - 1) / 2.0;
+    double jc[NL];          // sqrt(l(l+1) - (l-vi+1)(l-vi)),  hamil_2d.py:110
+    double dg0[NL];         // field-free diagonal
+#pragma unroll
+    for (int vi = 0; vi < NL; ++vi) {
+        jc[vi] = vi ? sqrt(lq * (lq + 1) - (lq - vi + 1) * (lq - vi)) : 0.0;
+        const double m = lq - vi;
+        if (p.hamil == 2) dg0[vi] = 2.0 * m * U + 2.0 * m * m * W;            // BH_X  hamil_2d.py:108-109
+        else if (p.hamil == 3) dg0[vi] = 2.0 * m * m * U;                      // BH_Z  hamil_2d.py:138-139
+        else if (p.hamil == 4) dg0[vi] = -2.0 * m * U + 2.0 * m * m * W;       // qubit hamil_2d.py:168-169
+        else dg0[vi] = p.vdiag[(long long)p.v_stride * run * NL + vi];         // two_levels hamil_2d.py:90-91
+    }
+
+    cd psi[NL], phi[NL], tmp[NL];
+    if (active) {
+#pragma unroll
+        for (int n = 0; n < NL; ++n) psi[n] = p.psi[((long long)run * p.nb + vec) * NL + n];
+    } else {
+#pragma unroll
+        for (int n = 0; n < NL; ++n) psi[n] = cmk(0.0, 0.0);
+    }
+    const long long erun = (long long)p.E_stride * run * (p.nt_max + 1);
+    const long long srun = (long long)p.s_stride * run * (p.nt_max + 1);
+    cd *E_out = p.E_out + (long long)run * (p.nt_max + 1);
+    const long long slice = (long long)NL * p.nthreads;
+
+    for (int l = p.l_first; l < p.l_first + p.nsteps; ++l) {
+        const bool live = active && l <= nt;
+        // ---- field -------------------------------------------------------------
+        cd E;
+        if (p.single_step) {
+            E = p.E_step[run];
+        } else if (p.field_mode == 0) {
+            const int le = p.reversed_E ? (l == 0 ? nt : nt - l + 1) : l;
+            E = (l <= nt) ? p.E_base[erun + le] : cmk(0.0, 0.0);
+        } else {
+            // UT forward (fitter.py:739-778): chi_tlist[-l] is slice nt+1-l of the backward record
+            cd part = cmk(0.0, 0.0);
+            if (live && l > 0) {
+                const cd *tr = p.traj_in + (long long)(nt + 1 - l) * slice + gt;
+#pragma unroll
+                for (int n = 0; n < NL; ++n) {
+                    const cd c = tr[(long long)n * p.nthreads];
+                    // a0[v] * cprod(chi, psi),  cprod(chi, psi) = dx * conj(psi) * chi  (math_base.py:21)
+                    part = cadd(part, cmul(a0, cscale(cmulc(c, psi[n]), dx)));
+                }
+            }
+            for (int o = 1; o < p.nbp; o <<= 1) {
+                part.x += __shfl_xor_sync(0xffffffffu, part.x, o);
+                part.y += __shfl_xor_sync(0xffffffffu, part.y, o);
+            }
+            if (l <= nt) {
+                const cd base = p.E_base[erun + l];
+                const double s = p.s_env[srun + l].x;
+                E = l > 0 ? cmk(base.x - s * part.y / h_lambda, base.y) : base;
+            } else {
+                E = cmk(0.0, 0.0);
+            }
+        }
+        if (live && vec == 0 && !p.single_step) {
+            E_out[l] = E;
+            if (p.write_E_base) p.E_base[erun + l] = E;
+        }
+        if (l == 0 || !live) continue;
+
+        // ---- level matrix for this field (rebuilt per step like hamil_2d.py:100-118) -------
+        double dg[NL];
+        cd up[NL], lo[NL];       // up[vi] = H[vi-1, vi], lo[vi] = H[vi, vi-1]
+#pragma unroll
+        for (int vi = 0; vi < NL; ++vi) {
+            dg[vi] = dg0[vi];
+            up[vi] = lo[vi] = cmk(0.0, 0.0);
+            if (p.hamil == 2) {                                            // BH_X: P = R = -delta*E*jc
+                up[vi] = lo[vi] = cscale(cscale(E, -delta), jc[vi]);
+            } else if (p.hamil == 3) {                                     // BH_Z: field on the diagonal
+                dg[vi] = dg0[vi] + 2.0 * (lq - vi) * E.x;
+                up[vi] = lo[vi] = cmk(-delta * jc[vi], 0.0);
+            } else if (p.hamil == 4) {                                     // qubit: P = -delta*E*jc, R = conj
+                up[vi] = cscale(cscale(E, -delta), jc[vi]);
+                lo[vi] = cmk(up[vi].x, -up[vi].y);
+            } else if (vi == 1) {                                          // two_levels: -E_full, -conj(E_full)
+                up[vi] = cmk(-E.x, -E.y);
+                lo[vi] = cmk(-E.x, E.y);
+            }
+        }
+        // ---- Newton recurrence ---------------------------------------------------------
+#pragma unroll
+        for (int n = 0; n < NL; ++n) {
+            phi[n] = psi[n];
+            psi[n] = cmul(psi[n], dv[0]);
+        }
+        for (int j = 0; j < p.nch - 1; ++j) {
+            const double xpj = p.xp[j];
+            const cd dvj = dv[j + 1];
+            tri_apply<NL>(dg, up, lo, phi, tmp);
+#pragma unroll
+            for (int n = 0; n < NL; ++n) {
+                cd r = cscale(tmp[n], c1);
+                r = csub(r, cscale(phi[n], c2));
+                r = cadd(cscale(phi[n], -xpj), r);
+                phi[n] = r;
+                psi[n] = cadd(psi[n], cmul(r, dvj));
+            }
+        }
+        double nsum = 0.0;
+        double nl[NL];
+#pragma unroll
+        for (int n = 0; n < NL; ++n) {
+            psi[n] = cmul(psi[n], phase);
+            nl[n] = (psi[n].x * psi[n].x + psi[n].y * psi[n].y) * dx;
+            nsum += nl[n];
+        }
+        if (!p.single_step) {
+            if (p.renorm && fabs(nsum) > 0.0) {
+                const double s = sqrt(fabs(nsum));
+#pragma unroll
+                for (int n = 0; n < NL; ++n) psi[n] = cmk(psi[n].x / s, psi[n].y / s);
+            }
+            if (l == nt || l == p.l_first + p.nsteps - 1) {
+#pragma unroll
+                for (int n = 0; n < NL; ++n) p.norms[((long long)run * p.nb + vec) * NL + n] = nl[n];
+            }
+            if (p.traj_out) {
+                cd *dst = p.traj_out + (long long)l * slice + gt;
+#pragma unroll
+                for (int n = 0; n < NL; ++n) dst[(long long)n * p.nthreads] = psi[n];
+            }
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int n = 0; n < NL; ++n) p.psi[((long long)run * p.nb + vec) * NL + n] = psi[n];
+    }
+}
+
+}  // namespace qc
