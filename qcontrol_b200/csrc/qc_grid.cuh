@@ -55,9 +55,11 @@ struct GridCfg {
     static constexpr int S1 = TPL + (R3 < 8 ? R3 : 0);   // padded row stride of the transpose buffers
     static constexpr int BUF = 16 * S1;         // complex elements per transpose buffer
     static constexpr int NTHREADS = 2 * TPL;
-    // shared memory (in complex elements): per level A, B, S ; tables tw1, tw2 ; then doubles
+    static constexpr int MAXCH = LOG2N == 11 ? 64 : 128;   // interpolation points that fit beside the buffers
+    static constexpr int TW1 = 15 * S1;         // twiddle rows k1 = 1..15 (row 0 is all ones and never read)
+    // shared memory (in complex elements): per level A, B, S ; tables tw1, tw2 ; then xp, dv, reduction scratch
     static constexpr size_t SMEM_BYTES =
-        sizeof(cd) * (size_t)(2 * (2 * BUF + N) + BUF + 16 * R3) + sizeof(double) * (size_t)(3 * 128 + 64);
+        sizeof(cd) * (size_t)(2 * (2 * BUF + N) + TW1 + 16 * R3) + sizeof(double) * (size_t)(3 * MAXCH + 32);
 };
 
 // skewed position of element (k2, n3) inside a lane group's private 16*R3 region
@@ -97,11 +99,11 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
     cd *bufB = bufA + BUF;
     cd *stash = bufB + BUF;
     const cd *stash_other = sm + (1 - lev) * (2 * BUF + N) + 2 * BUF;
-    cd *tw1 = sm + 2 * (2 * BUF + N);
-    cd *tw2 = tw1 + BUF;
-    double *s_xp = reinterpret_cast<double *>(tw2 + 16 * R3);
-    cd *s_dv = reinterpret_cast<cd *>(s_xp + 128);
-    double *s_red = s_xp + 3 * 128;              // 64 doubles of reduction scratch
+    cd *tw1 = sm + 2 * (2 * BUF + N) - S1;        // indexed [k1 * S1 + t] with k1 >= 1
+    cd *tw2 = sm + 2 * (2 * BUF + N) + C::TW1;
+    cd *s_dv = tw2 + 16 * R3;
+    double *s_xp = reinterpret_cast<double *>(s_dv + C::MAXCH);
+    double *s_red = s_xp + C::MAXCH;              // 32 doubles of reduction scratch
 
     const int run = blockIdx.x;
     if (run >= p.batch) return;
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
     const int n3p = t % R3;       // n3' (also the lane's index c inside its group in pass 3)
 
     // ---- tables -------------------------------------------------------------
-    for (int i = tid; i < BUF; i += C::NTHREADS) tw1[i] = p.tw1[i];
+    for (int i = S1 + tid; i < BUF; i += C::NTHREADS) tw1[i] = p.tw1[i];
     for (int i = tid; i < 16 * R3; i += C::NTHREADS) tw2[i] = p.tw2[i];
     const long long prun = (long long)p.poly_stride * run;
     for (int i = tid; i < p.nch; i += C::NTHREADS) {

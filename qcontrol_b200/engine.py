@@ -7,6 +7,7 @@ data and launches kernels; there is no arithmetic fallback here.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Optional, Sequence
 
 import numpy as np
@@ -45,8 +46,11 @@ class Context:
         self._h = C.c_void_p()
         check(lib.qc_create(int(device), C.c_void_p(stream) if stream else None, C.byref(self._h)))
         self.device = int(device)
+        self._plans = weakref.WeakSet()
 
     def close(self):
+        for pl in list(self._plans):      # plans hold a pointer to the context: they go first
+            pl.close()
         if self._h:
             lib.qc_destroy(self._h)
             self._h = C.c_void_p()
@@ -91,6 +95,7 @@ class Plan:
                      int(self.hf_hide), int(self.store_traj), 0)
         self._h = C.c_void_p()
         check(lib.qc_plan_create(ctx._h, C.byref(d), C.byref(self._h)))
+        ctx._plans.add(self)
         self.state_shape = (self.batch, self.nb, self.nlevs, self.np)
 
     def close(self):

@@ -393,11 +393,26 @@ def case_fitter_nlevel(R):
                   hamil2D=R.hamil_2d.Hamil2DQubit(tm.v, tm.akx2, conf.np, conf.U, conf.W, conf.delta, -2))
         tm.psi0, tm.psif = psi0, psif
 
+    def with_h(conf, h):
+        conf["fitter"]["h_lambda"] = h
+        return conf
+
+    # The shipped UT configurations other than the 2-level Jx one are ill-conditioned: the field update
+    # divides a round-off-sized overlap by a tiny h_lambda, and a 1-ulp change of psi0 moves the
+    # reference's own iteration table by 0.2 % ... 190 % (measured with the oracle).  The
+    # "_wc" variants raise h_lambda until the same code path is well-conditioned (sensitivity < 1e-12),
+    # so that a 1e-9 parity check is meaningful; the shipped values are kept for the feedback-free parts.
     for name, user, every, keep, patch in (
-            ("fit_ut_jx", conf_ut_jx(400, 3), 100, ("iter_0b/basis_0", "iter_0f/basis_1", "iter_3f/basis_0"), None),
-            ("fit_ut_jx_4lvls", conf_ut_jx(300, 2, nlevs=4, w_list=(0.3, 1.1, -0.6)), 100, ("iter_2f/basis_3",), None),
-            ("fit_ut_jz", conf_ut_jz(350, 3), 50, ("iter_3f/basis_1",), None),
-            ("fit_ut_s2s", conf_ut_s2s(350, 3), 50, ("iter_3f/basis_0",), None),
+            ("fit_ut_jx", conf_ut_jx(400, 3), 100, ("iter_0b/basis_0", "iter_0b/basis_1", "iter_0f/basis_1",
+                                                     "iter_3f/basis_0"), None),
+            ("fit_ut_jx_4lvls", conf_ut_jx(300, 2, nlevs=4, w_list=(0.3, 1.1, -0.6)), 100,
+             ("iter_0b/basis_0", "iter_0b/basis_3", "iter_2f/basis_3"), None),
+            ("fit_ut_jx_4lvls_wc", with_h(conf_ut_jx(300, 2, nlevs=4, w_list=(0.3, 1.1, -0.6)), 5e-4), 100,
+             ("iter_0b/basis_0", "iter_2f/basis_3"), None),
+            ("fit_ut_jz", conf_ut_jz(350, 3), 50, ("iter_0b/basis_0", "iter_0b/basis_1", "iter_3f/basis_1"), None),
+            ("fit_ut_jz_wc", with_h(conf_ut_jz(350, 3), 5e6), 50, ("iter_0b/basis_0", "iter_3f/basis_1"), None),
+            ("fit_ut_s2s", conf_ut_s2s(350, 3), 50, ("iter_0b/basis_0", "iter_3f/basis_0"), None),
+            ("fit_ut_s2s_wc", with_h(conf_ut_s2s(350, 3), 5e-4), 50, ("iter_0b/basis_0", "iter_3f/basis_0"), None),
             ("fit_pi_pulse", conf_pi_pulse(), 64, ("iter_0f/basis_0",), pi_patch)):
         conf, tm, fs, rep, err = run_fitter(R, user, every, patch)
         out = pack_fitter(rep, fs, tm, err, keep)

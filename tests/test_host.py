@@ -1,0 +1,145 @@
+"""Host-side logic of the product package against the oracle / reference goldens (CPU only):
+exact precompute (math_base), configuration DSL, task set-up, step scalars, batch enumeration."""
+import ast
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from oracle import qc_oracle as qo
+
+CONFS = ["fit_single_harm", "fit_single_morse", "fit_trans_woc", "fit_krotov_256", "fit_krotov_1024", "fit_ut_jx",
+         "fit_ut_jx_4lvls", "fit_ut_jz", "fit_ut_s2s", "fit_pi_pulse"]
+
+
+def _load(user):
+    from qcontrol_b200 import config, task_manager
+    with contextlib.redirect_stdout(io.StringIO()):
+        c = config.TaskRootConfiguration()
+        c.load(user)
+        return c, task_manager.create(c)
+
+
+def test_math_base_bit_exact(golden):
+    """The uploaded interpolation tables are the reference's, bit for bit (math_base.py:153-188)."""
+    from qcontrol_b200 import math_base as mb
+    g = golden("kat_math_base")
+    assert mb.reorder(8) == [0, 4, 2, 6, 1, 5, 3, 7] and mb.reorder(2) == [0, 1]
+    for nch in (2, 4, 8, 64):
+        assert mb.reorder(nch) == list(g["reorder_%d" % nch])
+    for nch, t in ((4, 1.0), (8, 5.65e-3), (8, -5.65e-3), (64, 0.2040), (64, 3.737), (64, -3.737), (64, 20.55)):
+        tag = "points_%d_%s" % (nch, repr(t).replace("-", "m").replace(".", "p"))
+        xp, dv = mb.points(nch, t, qo.func)
+        assert np.array_equal(xp, g[tag + "_xp"]) and np.array_equal(dv, g[tag + "_dv"])
+        xp2, dv2 = mb.newton_table(nch, t)
+        assert np.array_equal(xp2, xp) and np.array_equal(dv2, dv)
+        xb, db = mb.newton_tables_batched(nch, [t, 0.5 * t])
+        assert np.array_equal(xb, xp) and np.allclose(db[0], dv, rtol=0, atol=1e-18 + 1e-15 * np.abs(dv).max())
+    assert np.array_equal(mb.initak(4, 0.2, 2, 1), g["initak_4"])
+    assert np.array_equal(mb.initak(16, 0.3, 1, 1), g["initak_16_o1"])
+    assert np.array_equal(mb.initak(8, 0.3, 2, -2), g["initak_8_triv"])
+    s = np.array([1, 2, 3, 4])
+    assert mb.cprod(s, s, 0.2, 4) == 6 and mb.cprod2(np.ones(4), s, 0.2, 4) == 2     # reference math_base_tests.py:6-16
+    with pytest.raises(AssertionError):
+        mb.cprod(s, s[:3], 0.2, 4)
+
+
+@pytest.mark.parametrize("name", CONFS)
+def test_task_setup_bit_exact(golden, name):
+    """config.load + task_manager.create reproduce the reference's psi0 / psif / v / akx2 / grids exactly."""
+    g = golden(name)
+    c, tm = _load(ast.literal_eval(str(g["conf_json"])))
+    assert np.array_equal(tm.psi0.as_array(), g["psi0"])
+    if name != "fit_pi_pulse":                      # that test replaces the goal by hand (functional_tests.py:45-50)
+        assert np.array_equal(tm.psif.as_array(), g["psif"])
+    assert np.array_equal(np.stack([v[1] for v in tm.v]), g["v"])
+    assert np.array_equal(np.array([float(v[0]) for v in tm.v]), g["vmin"])
+    assert np.array_equal(tm.akx2, g["akx2"]) and np.array_equal(tm.x, g["x"])
+    assert float(tm.dx) == float(g["dx"]) and float(tm.t_step) == float(g["t_step"])
+
+
+def test_config_semantics():
+    from qcontrol_b200.config import TaskRootConfiguration as T
+    c = T()
+    with contextlib.redirect_stdout(io.StringIO()) as out:
+        c.load({"task_type": "optimal_control_krotov", "np": 256, "T": 1e-15, "unknown_key": 3,
+                "fitter": {"hf_hide": False, "propagation": {"nt": 10}}})
+    assert c.task_type == T.TaskType.OPTIMAL_CONTROL_KROTOV and c.np == 256 and isinstance(c.T, np.float64)
+    assert c.fitter.propagation.nt == 10 and c.fitter.propagation.nch == 64 and c.fitter.hf_hide == 0
+    assert "Parameter 'L' hasn't been provided" in out.getvalue()
+    assert T.TaskType.from_int(7) == T.TaskType.OPTIMAL_CONTROL_UNIT_TRANSFORM
+    with pytest.raises(KeyError):
+        T.TaskType.from_str("nonsense")
+    with pytest.raises(AttributeError):
+        c.no_such_field
+    c.fitter.w_list = [1.0]
+    assert c.fitter.w_list == [1.0]
+
+
+def test_factory_validation_errors():
+    base = {"task_type": "single_pot", "pot_type": "morse", "wf_type": "morse", "hamil_type": "ntriv", "np": 256,
+            "fitter": {"propagation": {"nt": 4}}}
+    for patch, exc in (({"nlevs": 3}, RuntimeError), ({"nb": 2}, RuntimeError), ({"hamil_type": "two_levels", "nb": 2,
+                                                                                   "fitter": {"hf_hide": False}}, RuntimeError),
+                       ({"init_guess_hf": "cos"}, RuntimeError)):
+        user = dict(base)
+        user.update(patch)
+        with pytest.raises(exc):
+            _load(user)
+    with pytest.raises(RuntimeError):
+        _load({"task_type": "optimal_control_unit_transform", "pot_type": "none", "np": 1, "hamil_type": "BH_model",
+               "fitter": {"hf_hide": True}})
+
+
+@pytest.mark.parametrize("name", ["harm", "morse", "krotov"])
+def test_energy_window_matches_reference(golden, name):
+    """emax / emin / t_sc of PropagationSolver.step (propagation.py:371-407) as recorded from the reference."""
+    from qcontrol_b200 import control
+    from tests.golden.gen_golden import conf_krotov, conf_single_harm, conf_single_morse
+    g = golden("one_step_" + name)
+    user = {"harm": conf_single_harm(2000), "morse": conf_single_morse(2000), "krotov": conf_krotov(2000, 1)}[name]
+    pb = qo.make_problem(user)
+    emax, emin, t_sc, eL = control.energy_window(pb)
+    assert (float(emax), float(emin), float(t_sc), float(eL)) == (float(g["emax"]), float(g["emin"]), float(g["t_sc"]),
+                                                                  float(g["eL"]))
+    _, _, t_b, _ = control.energy_window(pb, control.BACKWARD)
+    assert float(t_b) == -float(t_sc)
+
+
+def test_substitution_expansion_order():
+    """@SUBST:LIST expansion: Cartesian product, first list fastest (json_substitutions.py:70-99);
+    the shipped 25 x 16 T-sweep expands to 400 variants."""
+    from qcontrol_b200 import batch
+    t = {"run_id": {"@SUBST:LIST": ["a", "b", "c"]}, "T": {"@SUBST:LIST": [1.0, 2.0]}, "fitter": {"x": [1, {"@SUBST:LIST": [7, 8]}]}}
+    v = batch.expand_substitutions(t)
+    assert len(v) == 12
+    assert [(d["run_id"], d["T"], d["fitter"]["x"][1]) for d in v[:4]] == [("a", 1.0, 7), ("b", 1.0, 7), ("c", 1.0, 7), ("a", 2.0, 7)]
+    assert v[-1] == {"run_id": "c", "T": 2.0, "fitter": {"x": [1, 8]}}
+    assert batch.expand_substitutions({"a": 1}) == [{"a": 1}]
+    assert batch.expand_substitutions({"a": {"@SUBST:LIST": []}}) == []
+    sweep = {"run_id": {"@SUBST:LIST": ["ut/run%d" % i for i in range(1, 26)]}, "T": {"@SUBST:LIST": [2.5e-13] + [1e-12] * 15}}
+    assert len(batch.expand_substitutions(sweep)) == 400
+
+
+def test_auto_rules_and_seeded_w_list():
+    from qcontrol_b200 import batch
+    from tests.golden.gen_golden import conf_ut_jx
+    user = conf_ut_jx(1, 1, T=11.8e-12)
+    user["nt_auto"] = True
+    user["fitter"]["w_list"] = []
+    c, _ = _load(user)
+    batch.apply_auto_rules(c, run_index=3)
+    assert c.fitter.propagation.nt == 5900 and float(c.fitter.propagation.sigma) == 2.0 * 11.8e-12
+    assert np.array_equal(c.fitter.w_list, np.random.default_rng(1003).uniform(-2.0, 2.0, 3))
+
+
+def test_lpt_sharding_is_balanced_and_deterministic():
+    from qcontrol_b200 import batch
+    nts = [125, 5900, 6700, 7000, 7500, 8300, 8400, 8500, 8800, 8900, 9000, 9100, 9200, 9300, 9400, 9500] * 25
+    shards = batch.lpt_shards(nts, 8)
+    assert sorted(i for s in shards for i in s) == list(range(400))
+    loads = [sum(nts[i] for i in s) for s in shards]
+    assert max(loads) / min(loads) < 1.01
+    assert shards == batch.lpt_shards(nts, 8)
+    assert batch.lpt_shards([3.0], 4) == [[0], [], [], []]

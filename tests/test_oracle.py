@@ -151,7 +151,8 @@ def _run_and_compare(pb, g, keep=(), tol=0.0):
     return fit
 
 
-@pytest.mark.parametrize("name", ["fit_ut_jx", "fit_ut_jx_4lvls", "fit_ut_jz", "fit_ut_s2s"])
+@pytest.mark.parametrize("name", ["fit_ut_jx", "fit_ut_jx_4lvls", "fit_ut_jz", "fit_ut_s2s", "fit_ut_jx_4lvls_wc",
+                                  "fit_ut_jz_wc", "fit_ut_s2s_wc"])
 def test_unit_transform_bitexact(golden, name):
     """Whole optimisation loops on N-level systems: backward/forward sweeps,
     field update from the stored trajectory, dynamic h_lambda, F / E_int / J."""
