@@ -386,8 +386,6 @@ extern "C" int32_t qc_plan_create(qc_context *ctx, const qc_plan_desc *desc, qc_
     if (grid) {
         if (!is_pow2(d.np) || d.np < 256 || d.np > 2048)
             return fail(QC_ERR_ARG, "qc_plan_create: grid plans need np in {256,512,1024,2048}, got %d", d.np);
-        if (d.np == 2048 && d.nch > 64)
-            return fail(QC_ERR_ARG, "qc_plan_create: np=2048 plans hold at most nch=64 interpolation points in shared memory");
         if (d.nlevs != 2 || d.nb != 1)
             return fail(QC_ERR_ARG, "qc_plan_create: the FFT-grid Hamiltonian has nlevs=2, nb=1 (task_manager.py:925-932)");
     } else {

@@ -11,6 +11,16 @@
 // FFT: N = 16*16*R3 (R3 = N/256), decimation in frequency forward, the exact
 // mirror inverse, so no reordering pass is needed and the k-space multiply runs
 // on the permuted layout with a per-thread register copy of the multiplier.
+// Twiddles are NOT read from a table: shared-memory bandwidth is the binding
+// resource of this kernel (ncu, profiles/r01a_*), the FP64 pipe has slack, so
+// each thread keeps the two roots it needs (w_N^t and w_{16 R3}^{n3}) in
+// registers and generates their powers with a running complex product.
+//
+// Synchronisation (N >= 512): the two levels are separate groups of warps that
+// only meet at the coupling term -E*phi_other.  Each level synchronises its own
+// transposes on a private named barrier; the phi stash is handed over with a
+// full/released pair of named barriers (bar.arrive / bar.sync), so neither level
+// ever waits for the other unless it is a whole polynomial order ahead.
 #pragma once
 #include "qc_fft.cuh"
 
@@ -25,8 +35,8 @@ struct GridParams {
     const double *v;             // [vb][2][N]
     long long v_stride;
     const double *kin;           // [N]
-    const cd *tw1;               // [16][S1]
-    const cd *tw2;               // [16][R3]
+    const cd *tw1;               // [16][S1]  (row 1 = w_N^t is the only row the kernel reads)
+    const cd *tw2;               // [16][R3]  (row 1 = w_{16 R3}^{n3})
     const double *xp;            // [nch]
     const cd *dv;                // [pb][nch]
     const double *sc;            // [pb][4] emin emax t_sc eL
@@ -55,17 +65,36 @@ struct GridCfg {
     static constexpr int S1 = TPL + (R3 < 8 ? R3 : 0);   // padded row stride of the transpose buffers
     static constexpr int BUF = 16 * S1;         // complex elements per transpose buffer
     static constexpr int NTHREADS = 2 * TPL;
-    static constexpr int MAXCH = LOG2N == 11 ? 64 : 128;   // interpolation points that fit beside the buffers
-    static constexpr int TW1 = 15 * S1;         // twiddle rows k1 = 1..15 (row 0 is all ones and never read)
-    // shared memory (in complex elements): per level A, B, S ; tables tw1, tw2 ; then xp, dv, reduction scratch
+    static constexpr int MAXCH = 128;
+    static constexpr bool NAMED = TPL >= 32;    // a level is made of whole warps: per-level named barriers
+    // shared memory (complex elements): per level A, B, S ; then dv, xp, reduction scratch
     static constexpr size_t SMEM_BYTES =
-        sizeof(cd) * (size_t)(2 * (2 * BUF + N) + TW1 + 16 * R3) + sizeof(double) * (size_t)(3 * MAXCH + 32);
+        sizeof(cd) * (size_t)(2 * (2 * BUF + N)) + sizeof(double) * (size_t)(3 * MAXCH + 32);
 };
 
 // skewed position of element (k2, n3) inside a lane group's private 16*R3 region
 template <int R3, int Q>
 __device__ __forceinline__ int pos2(int k2, int n3) {
     return k2 * R3 + ((n3 + k2 / Q) & (R3 - 1));
+}
+
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// a[k] *= w^k (k = 1..15) with a running product; conjugated for the inverse transform
+template <bool INV>
+__device__ __forceinline__ void twiddle_powers(cd *a, const cd w) {
+    cd pw = w;
+    a[1] = twmul<INV>(a[1], pw);
+#pragma unroll
+    for (int k = 2; k < 16; ++k) {
+        pw = cmul(pw, w);
+        a[k] = twmul<INV>(a[k], pw);
+    }
 }
 
 // Sum `val` over the threads of each level; every thread gets both sums.
@@ -90,6 +119,7 @@ template <int LOG2N>
 __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel(GridParams p) {
     typedef GridCfg<LOG2N> C;
     constexpr int N = C::N, TPL = C::TPL, R3 = C::R3, Q = C::Q, S1 = C::S1, BUF = C::BUF;
+    constexpr bool NAMED = C::NAMED;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd *sm = reinterpret_cast<cd *>(smem_raw);
     const int tid = threadIdx.x;
@@ -99,9 +129,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
     cd *bufB = bufA + BUF;
     cd *stash = bufB + BUF;
     const cd *stash_other = sm + (1 - lev) * (2 * BUF + N) + 2 * BUF;
-    cd *tw1 = sm + 2 * (2 * BUF + N) - S1;        // indexed [k1 * S1 + t] with k1 >= 1
-    cd *tw2 = sm + 2 * (2 * BUF + N) + C::TW1;
-    cd *s_dv = tw2 + 16 * R3;
+    cd *s_dv = sm + 2 * (2 * BUF + N);
     double *s_xp = reinterpret_cast<double *>(s_dv + C::MAXCH);
     double *s_red = s_xp + C::MAXCH;              // 32 doubles of reduction scratch
 
@@ -109,10 +137,10 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
     if (run >= p.batch) return;
     const int k1p = t / R3;       // k1' : which pass-1 output row this thread transforms in pass 2
     const int n3p = t % R3;       // n3' (also the lane's index c inside its group in pass 3)
+    // named barrier ids: 1,2 level-local transposes; 3,4 "stash of level n is full"; 5,6 "... released"
+    const int BAR_LEVEL = 1 + lev, BAR_FULL_OWN = 3 + lev, BAR_FULL_OTH = 4 - lev, BAR_REL_OWN = 5 + lev,
+              BAR_REL_OTH = 6 - lev;
 
-    // ---- tables -------------------------------------------------------------
-    for (int i = S1 + tid; i < BUF; i += C::NTHREADS) tw1[i] = p.tw1[i];
-    for (int i = tid; i < 16 * R3; i += C::NTHREADS) tw2[i] = p.tw2[i];
     const long long prun = (long long)p.poly_stride * run;
     for (int i = tid; i < p.nch; i += C::NTHREADS) {
         s_xp[i] = p.xp[i];
@@ -128,6 +156,8 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
     double ph_s, ph_c;
     sincos(-2.0 * t_sc * (emax + emin) / (emax - emin), &ph_s, &ph_c);   // phys_base.py:174
     const cd phase = cmk(ph_c, ph_s);
+    const cd w1 = p.tw1[S1 + t];            // w_N^t          (forward value)
+    const cd w2 = p.tw2[R3 + n3p];          // w_{16 R3}^{n3'}
 
     // per-thread constants: diagonal d(x) = c1*(v(x) +- eL) - c2 and k-space multiplier
     double dcoef[16], kc[16];
@@ -161,6 +191,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
     // which level records / reads trajectories: forward sweeps record level 0 and read the stored
     // level 1 of chi; backward sweeps record level 1 and read level 0 of psi (fitter.py:700-706, 791-796)
     const int ov_lev = p.field_mode == 2 ? 1 : 0;
+    const int last_j = p.nch - 2;
 
     for (int l = p.l_first; l < p.l_first + p.nsteps && l <= nt; ++l) {
         const bool start_only = (l == 0);   // start(): only the initial field is evaluated (propagation.py:360-361)
@@ -215,26 +246,29 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
             a[i] = psi[i];
             psi[i] = cmul(psi[i], s_dv[0]);
         }
-        for (int j = 0; j < p.nch - 1; ++j) {
+        for (int j = 0; j <= last_j; ++j) {
             const double xpj = s_xp[j];
             const cd dvj = s_dv[j + 1];
-            // stash phi (own slots, natural x order)
+            // stash phi (own slots, natural x order) once the other level has read the previous one
+            if (NAMED && j > 0) bar_sync(BAR_REL_OWN, C::NTHREADS);
 #pragma unroll
             for (int n1 = 0; n1 < 16; ++n1) stash[t + TPL * n1] = a[n1];
+            if (NAMED) {
+                __threadfence_block();
+                bar_arrive(BAR_FULL_OWN, C::NTHREADS);
+            }
             // pass 1 : DFT over n1, twiddle w_N^(k1*t)
             dft16<false>(a);
-#pragma unroll
-            for (int k1 = 1; k1 < 16; ++k1) a[k1] = cmul(a[k1], tw1[k1 * S1 + t]);
+            twiddle_powers<false>(a, w1);
 #pragma unroll
             for (int k1 = 0; k1 < 16; ++k1) bufA[k1 * S1 + t] = a[k1];
-            __syncthreads();                                                       // (#1)
+            if (NAMED) bar_sync(BAR_LEVEL, TPL); else __syncthreads();              // (#1)
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) a[n2] = bufA[k1p * S1 + n2 * R3 + n3p];
             // pass 2 : DFT over n2, twiddle w_{16 R3}^(k2*n3)
             dft16<false>(a);
             if (R3 > 1) {
-#pragma unroll
-                for (int k2 = 1; k2 < 16; ++k2) a[k2] = cmul(a[k2], tw2[k2 * R3 + n3p]);
+                twiddle_powers<false>(a, w2);
                 __syncwarp();
 #pragma unroll
                 for (int k2 = 0; k2 < 16; ++k2) bufA[k1p * S1 + pos2<R3, Q>(k2, n3p)] = a[k2];
@@ -257,35 +291,37 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
                 __syncwarp();
 #pragma unroll
                 for (int k2 = 0; k2 < 16; ++k2) a[k2] = bufB[k1p * S1 + pos2<R3, Q>(k2, n3p)];
-#pragma unroll
-                for (int k2 = 1; k2 < 16; ++k2) a[k2] = cmulc(a[k2], tw2[k2 * R3 + n3p]);
+                twiddle_powers<true>(a, w2);
                 __syncwarp();
             }
             // inverse pass 2
             dft16<true>(a);
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) bufB[k1p * S1 + n2 * R3 + n3p] = a[n2];
-            __syncthreads();                                                       // (#2)
+            if (NAMED) bar_sync(BAR_LEVEL, TPL); else __syncthreads();              // (#2)
 #pragma unroll
             for (int k1 = 0; k1 < 16; ++k1) a[k1] = bufB[k1 * S1 + t];
-#pragma unroll
-            for (int k1 = 1; k1 < 16; ++k1) a[k1] = cmulc(a[k1], tw1[k1 * S1 + t]);
+            twiddle_powers<true>(a, w1);
             // inverse pass 1 -> kinetic term (already scaled by c1) at x = t + TPL*n1
             dft16<true>(a);
             // pointwise part (hamil_2d.py:60-71, phys_base.py:98-111) and accumulation (phys_base.py:170-172)
-            const double shift = xpj;
+            if (NAMED) bar_sync(BAR_FULL_OTH, C::NTHREADS);
 #pragma unroll
             for (int n1 = 0; n1 < 16; ++n1) {
                 const cd own = stash[t + TPL * n1];
                 const cd oth = stash_other[t + TPL * n1];
-                const double dd = dcoef[n1] - shift;
+                const double dd = dcoef[n1] - xpj;
                 cd r;
                 r.x = fma(dd, own.x, fma(-cE, oth.x, a[n1].x));
                 r.y = fma(dd, own.y, fma(-cE, oth.y, a[n1].y));
                 a[n1] = r;
                 psi[n1] = cfma(dvj, r, psi[n1]);
             }
-            __syncthreads();                                                       // (#3) stash reuse
+            if (NAMED) {
+                if (j < last_j) bar_arrive(BAR_REL_OTH, C::NTHREADS);
+            } else {
+                __syncthreads();                                                   // (#3) stash reuse
+            }
         }
         // ---- final phase (phys_base.py:174-176), norms, renormalisation --------
         double nrm = 0.0;
@@ -310,7 +346,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
                 for (int i = 0; i < 16; ++i) psi[i] = cmk(psi[i].x / s, psi[i].y / s);
             }
             // ---- record the rotating-frame state (fitter.py:301-309, 322-329) -----
-            if (traj_out && lev == (p.field_mode == 2 ? 1 : 0)) {
+            if (traj_out && lev == ov_lev) {
                 cd *dst = traj_out + (long long)l * N;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) dst[t + TPL * i] = psi[i];
@@ -328,6 +364,8 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
                     }
                 }
             }
+        } else {
+            __syncthreads();
         }
     }
     {
