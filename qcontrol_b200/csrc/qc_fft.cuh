@@ -123,6 +123,104 @@ __device__ __forceinline__ void dft16(cd *a) {
         }
 }
 
+
+// ---- 16-point DFT split into its two radix-4 stages, so that twiddling and the shared-memory
+// ---- traffic around it can be streamed group by group (keeps register live ranges short)
+template <bool INV>
+__device__ __forceinline__ void dft16_internal_twiddles(cd *a) {
+    const cd w1 = cmk(QC_COS_PI_8, -QC_SIN_PI_8);   // w16^1
+    const cd w3 = cmk(QC_SIN_PI_8, -QC_COS_PI_8);   // w16^3
+    const cd w9 = cmk(-QC_COS_PI_8, QC_SIN_PI_8);   // w16^9
+    a[5] = twmul<INV>(a[5], w1);
+    a[6] = mul_w8_1<INV>(a[6]);
+    a[7] = twmul<INV>(a[7], w3);
+    a[9] = mul_w8_1<INV>(a[9]);
+    a[10] = mul_mi<INV>(a[10]);
+    a[11] = mul_w8_3<INV>(a[11]);
+    a[13] = twmul<INV>(a[13], w3);
+    a[14] = mul_w8_3<INV>(a[14]);
+    a[15] = twmul<INV>(a[15], w9);
+}
+
+struct TwBase {       // w^0..w^3 and q = w^4 of one root
+    cd b1, b2, b3, q;
+};
+__device__ __forceinline__ TwBase tw_base(cd w_in) {
+    double wx = w_in.x, wy = w_in.y;
+    asm volatile("" : "+d"(wx), "+d"(wy));      // the root is loop invariant: keep its powers from being hoisted
+    TwBase t;
+    t.b1 = cmk(wx, wy);
+    t.b2 = cmul(t.b1, t.b1);
+    t.b3 = cmul(t.b2, t.b1);
+    t.q = cmul(t.b2, t.b2);
+    return t;
+}
+
+// a (natural order) -> DFT16 -> element k multiplied by w^k -> sink(k, value), k in groups {ka, ka+4, ka+8, ka+12}
+template <bool INV, class Sink>
+__device__ __forceinline__ void dft16_twiddle_out(cd *a, const cd w, Sink sink) {
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) dft4<INV>(a[nb], a[4 + nb], a[8 + nb], a[12 + nb]);
+    dft16_internal_twiddles<INV>(a);
+    const TwBase tb = tw_base(w);
+#pragma unroll
+    for (int ka = 0; ka < 4; ++ka) {
+        dft4<INV>(a[4 * ka], a[4 * ka + 1], a[4 * ka + 2], a[4 * ka + 3]);   // X[ka + 4 kb] in a[4 ka + kb]
+        cd r = ka == 0 ? tb.q : (ka == 1 ? tb.b1 : (ka == 2 ? tb.b2 : tb.b3));
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+            if (ka == 0 && kb == 0) {
+                sink(0, a[0]);
+            } else {
+                sink(ka + 4 * kb, cmul(a[4 * ka + kb], r));
+                if (kb < 3) r = cmul(r, tb.q);
+            }
+        }
+    }
+}
+
+// source(k) * conj(w^k) -> inverse DFT16 -> a (natural order); loads come in groups {nb, nb+4, nb+8, nb+12}
+template <class Source>
+__device__ __forceinline__ void dft16_twiddle_in_inv(cd *a, const cd w, Source source) {
+    const TwBase tb = tw_base(w);
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+        cd r = nb == 0 ? tb.q : (nb == 1 ? tb.b1 : (nb == 2 ? tb.b2 : tb.b3));
+        cd x0 = source(nb), x1 = source(nb + 4), x2 = source(nb + 8), x3 = source(nb + 12);
+        if (nb == 0) {
+            x1 = cmulc(x1, r);
+            r = cmul(r, tb.q);
+            x2 = cmulc(x2, r);
+            r = cmul(r, tb.q);
+            x3 = cmulc(x3, r);
+        } else {
+            x0 = cmulc(x0, r);
+            r = cmul(r, tb.q);
+            x1 = cmulc(x1, r);
+            r = cmul(r, tb.q);
+            x2 = cmulc(x2, r);
+            r = cmul(r, tb.q);
+            x3 = cmulc(x3, r);
+        }
+        dft4<true>(x0, x1, x2, x3);
+        a[nb] = x0;
+        a[4 + nb] = x1;
+        a[8 + nb] = x2;
+        a[12 + nb] = x3;
+    }
+    dft16_internal_twiddles<true>(a);
+#pragma unroll
+    for (int ka = 0; ka < 4; ++ka) dft4<true>(a[4 * ka], a[4 * ka + 1], a[4 * ka + 2], a[4 * ka + 3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = i + 1; j < 4; ++j) {
+            cd t = a[4 * i + j];
+            a[4 * i + j] = a[4 * j + i];
+            a[4 * j + i] = t;
+        }
+}
+
 template <int R, bool INV>
 __device__ __forceinline__ void dft(cd *a) {
     if (R == 2) dft2<INV>(a[0], a[1]);

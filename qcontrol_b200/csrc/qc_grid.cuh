@@ -67,9 +67,9 @@ struct GridCfg {
     static constexpr int NTHREADS = 2 * TPL;
     static constexpr int MAXCH = 128;
     static constexpr bool NAMED = TPL >= 32;    // a level is made of whole warps: per-level named barriers
-    // shared memory (complex elements): per level A, B, S ; then dv, xp, reduction scratch
+    // shared memory (complex elements): per level A, B, S ; then dv, xp, reduction scratch, k-space multiplier
     static constexpr size_t SMEM_BYTES =
-        sizeof(cd) * (size_t)(2 * (2 * BUF + N)) + sizeof(double) * (size_t)(3 * MAXCH + 32);
+        sizeof(cd) * (size_t)(2 * (2 * BUF + N)) + sizeof(double) * (size_t)(3 * MAXCH + 32 + N);
 };
 
 // skewed position of element (k2, n3) inside a lane group's private 16*R3 region
@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
     cd *s_dv = sm + 2 * (2 * BUF + N);
     double *s_xp = reinterpret_cast<double *>(s_dv + C::MAXCH);
     double *s_red = s_xp + C::MAXCH;              // 32 doubles of reduction scratch
+    double *s_kc = s_red + 32;                    // [16][TPL] k-space multiplier in this thread layout (both levels)
 
     const int run = blockIdx.x;
     if (run >= p.batch) return;
@@ -159,8 +160,12 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
     const cd w1 = p.tw1[S1 + t];            // w_N^t          (forward value)
     const cd w2 = p.tw2[R3 + n3p];          // w_{16 R3}^{n3'}
 
-    // per-thread constants: diagonal d(x) = c1*(v(x) +- eL) - c2 and k-space multiplier
-    double dcoef[16], kc[16];
+    // per-thread constants: diagonal d(x) = c1*(v(x) +- eL) - c2 (registers) and the k-space multiplier
+    // (shared memory: the register file cannot hold it beside phi, psi and d without spilling)
+    double dcoef[16];
+#ifdef QC_KC_REGS
+    double kc[16];
+#endif
     {
         const double *vr = p.v + p.v_stride * run + (long long)lev * N;
         const double sgn = lev == 0 ? eL : -eL;                  // hamil_2d.py:50-51, 66-67
@@ -171,7 +176,11 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
         for (int e = 0; e < 16; ++e) {
             const int q = e / R3, k3 = e % R3;
             const int k = k1p + 16 * (n3p * Q + q) + 256 * k3;
+#ifdef QC_KC_REGS
             kc[e] = p.kin[k] * kscale;
+#else
+            if (lev == 0) s_kc[e * TPL + t] = p.kin[k] * kscale;
+#endif
         }
     }
 
@@ -249,29 +258,23 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
         for (int j = 0; j <= last_j; ++j) {
             const double xpj = s_xp[j];
             const cd dvj = s_dv[j + 1];
+            // keep the swizzled transpose addresses from being hoisted out of the loop (64 registers):
+            // they are two integer instructions each on an otherwise idle pipe
             // stash phi (own slots, natural x order) once the other level has read the previous one
             if (NAMED && j > 0) bar_sync(BAR_REL_OWN, C::NTHREADS);
 #pragma unroll
             for (int n1 = 0; n1 < 16; ++n1) stash[t + TPL * n1] = a[n1];
-            if (NAMED) {
-                __threadfence_block();
-                bar_arrive(BAR_FULL_OWN, C::NTHREADS);
-            }
+            if (NAMED) bar_arrive(BAR_FULL_OWN, C::NTHREADS);   // producer side of a named barrier: no fence (FA3 pattern)
             // pass 1 : DFT over n1, twiddle w_N^(k1*t)
-            dft16<false>(a);
-            twiddle_powers<false>(a, w1);
-#pragma unroll
-            for (int k1 = 0; k1 < 16; ++k1) bufA[k1 * S1 + t] = a[k1];
+            dft16_twiddle_out<false>(a, w1, [&](int k1, cd val) { bufA[k1 * S1 + t] = val; });
             if (NAMED) bar_sync(BAR_LEVEL, TPL); else __syncthreads();              // (#1)
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) a[n2] = bufA[k1p * S1 + n2 * R3 + n3p];
             // pass 2 : DFT over n2, twiddle w_{16 R3}^(k2*n3)
-            dft16<false>(a);
+            if (R3 == 1) dft16<false>(a);
             if (R3 > 1) {
-                twiddle_powers<false>(a, w2);
                 __syncwarp();
-#pragma unroll
-                for (int k2 = 0; k2 < 16; ++k2) bufA[k1p * S1 + pos2<R3, Q>(k2, n3p)] = a[k2];
+                dft16_twiddle_out<false>(a, w2, [&](int k2, cd val) { bufA[k1p * S1 + pos2<R3, Q>(k2, n3p)] = val; });
                 __syncwarp();
 #pragma unroll
                 for (int e = 0; e < 16; ++e)
@@ -281,7 +284,11 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
                 for (int q = 0; q < Q; ++q) dft<R3, false>(a + q * R3);
             }
 #pragma unroll
+#ifdef QC_KC_REGS
             for (int e = 0; e < 16; ++e) a[e] = cscale(a[e], kc[e]);
+#else
+            for (int e = 0; e < 16; ++e) a[e] = cscale(a[e], s_kc[e * TPL + t]);
+#endif
             if (R3 > 1) {
 #pragma unroll
                 for (int q = 0; q < Q; ++q) dft<R3, true>(a + q * R3);
@@ -289,33 +296,34 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
                 for (int e = 0; e < 16; ++e)
                     bufB[k1p * S1 + pos2<R3, Q>(n3p * Q + e / R3, e % R3)] = a[e];
                 __syncwarp();
-#pragma unroll
-                for (int k2 = 0; k2 < 16; ++k2) a[k2] = bufB[k1p * S1 + pos2<R3, Q>(k2, n3p)];
-                twiddle_powers<true>(a, w2);
+                dft16_twiddle_in_inv(a, w2, [&](int k2) { return bufB[k1p * S1 + pos2<R3, Q>(k2, n3p)]; });
                 __syncwarp();
             }
             // inverse pass 2
-            dft16<true>(a);
+            if (R3 == 1) dft16<true>(a);
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) bufB[k1p * S1 + n2 * R3 + n3p] = a[n2];
             if (NAMED) bar_sync(BAR_LEVEL, TPL); else __syncthreads();              // (#2)
-#pragma unroll
-            for (int k1 = 0; k1 < 16; ++k1) a[k1] = bufB[k1 * S1 + t];
-            twiddle_powers<true>(a, w1);
             // inverse pass 1 -> kinetic term (already scaled by c1) at x = t + TPL*n1
-            dft16<true>(a);
+            dft16_twiddle_in_inv(a, w1, [&](int k1) { return bufB[k1 * S1 + t]; });
             // pointwise part (hamil_2d.py:60-71, phys_base.py:98-111) and accumulation (phys_base.py:170-172)
             if (NAMED) bar_sync(BAR_FULL_OTH, C::NTHREADS);
+            // in chunks of four grid points: the compiler otherwise hoists all 32 shared loads above the
+            // arithmetic and spills (the register file holds phi, psi and d with little to spare)
 #pragma unroll
-            for (int n1 = 0; n1 < 16; ++n1) {
-                const cd own = stash[t + TPL * n1];
-                const cd oth = stash_other[t + TPL * n1];
-                const double dd = dcoef[n1] - xpj;
-                cd r;
-                r.x = fma(dd, own.x, fma(-cE, oth.x, a[n1].x));
-                r.y = fma(dd, own.y, fma(-cE, oth.y, a[n1].y));
-                a[n1] = r;
-                psi[n1] = cfma(dvj, r, psi[n1]);
+            for (int c4 = 0; c4 < 16; c4 += 4) {
+#pragma unroll
+                for (int n1 = c4; n1 < c4 + 4; ++n1) {
+                    const cd own = stash[t + TPL * n1];
+                    const cd oth = stash_other[t + TPL * n1];
+                    const double dd = dcoef[n1] - xpj;
+                    cd r;
+                    r.x = fma(dd, own.x, fma(-cE, oth.x, a[n1].x));
+                    r.y = fma(dd, own.y, fma(-cE, oth.y, a[n1].y));
+                    a[n1] = r;
+                    psi[n1] = cfma(dvj, r, psi[n1]);
+                }
+                asm volatile("" ::: "memory");
             }
             if (NAMED) {
                 if (j < last_j) bar_arrive(BAR_REL_OTH, C::NTHREADS);
