@@ -152,6 +152,25 @@ int32_t qc_sweep(qc_plan *plan, const qc_sweep_args *args);
  * orig=False) (phys_base.py:129-178).  E[batch] complex (real part used on the grid). Synchronous. */
 int32_t qc_prop_step(qc_plan *plan, int32_t poly_slot, const double *E);
 
+/* One application of an operator to the resident state, result to the host, state unchanged:
+ *   which = 0  phi = H psi : the functor call hamil2D(orig, psi, E, eL, E_full) (hamil_2d.py:190-223);
+ *              E[batch] complex is E (orig = 0, real part used on the grid) or E_full (orig = 1)
+ *   which = 1  phi = T psi = ifft(akx2 * fft(psi))             (phys_base.diff_cpu, phys_base.py:18-36)
+ *   which = 2  phi = P psi with the momentum multiplier of qc_set_instr_grid   (phys_base.py:238-244)
+ * out[batch][nb][nlevs][np] complex. */
+int32_t qc_apply_hamil(qc_plan *plan, int32_t which, int32_t orig, const double *E, double eL, double *out);
+
+/* Grid data only the instrumentation needs: x[np] and the real momentum multiplier
+ * akx[np] = initak(np, dx, 1, ntriv) * hart_to_cm / (-i) / dalt_to_au  (phys_base.py:238-240); akx may be NULL. */
+int32_t qc_set_instr_grid(qc_plan *plan, const double *x, const double *akx_re);
+
+/* The instrumentation block of PropagationSolver.step (propagation.py:462-470) on the device:
+ * out[batch][nb][nlevs][20] = cnorm(2) cener(2) overlp0(2) overlpf(2) <x>(2) <x^2>(2) <p>(2) <p^2>(2)
+ * max|psi|, Re psi at argmax|Re psi|, cprod(psi_0, psi_1)(2).  E_full[batch] complex (may be NULL = 0);
+ * two_m = 2*m; psi0_slot / psif_slot: snapshot slots of psi0 / psif (-1 to skip). */
+int32_t qc_instrument(qc_plan *plan, const double *E_full, double two_m, int32_t psi0_slot, int32_t psif_slot,
+                      double *out);
+
 /* Field used at each step of the last sweep(s): E_out[batch][nt_max+1] complex (E_tlist, fitter.py:281,326). */
 int32_t qc_get_fields(qc_plan *plan, double *E_out);
 /* Per-level norms before renormalisation, norms[batch][nb][nlevs] of the LAST step run (cnorm, propagation.py:424-429). */

@@ -144,6 +144,31 @@ class _BatchBase:
         self.plan.set_poly(slot, xp, dvs, np.array(emins), np.array(emaxs), np.array(tscs), np.array(eLs))
         self._poly_dir[direction] = slot
 
+    observer = None      # callable(prop_id, l, direction, snapshots) invoked at l = 0 and every `stride` steps
+    stride = 1
+
+    def _sweep(self, prop_id, direction, snaps, slot, mode, l_first, nsteps, tr, tw, **kw):
+        """One sweep launch, or -- when an observer is attached -- the same sweep cut into chunks that end
+        on the steps the observer wants to see (the reporters of the reference are called every step and
+        keep every mod-th one, propagation.py:291-299; here only those steps cost a host round trip)."""
+        pl = self.plan
+        if self.observer is None:
+            pl.sweep(slot, mode, l_first, nsteps, True, tr, tw, **kw)
+            return
+        end = l_first + nsteps
+        l = l_first
+        if l == 0:
+            pl.sweep(slot, mode, 0, 1, True, tr, tw, **kw)
+            l = 1
+        self.observer(prop_id, 0, direction, snaps)
+        stride = max(1, int(self.stride))
+        while l < end:
+            nxt = min(end, ((l - 1) // stride + 1) * stride + 1)
+            pl.sweep(slot, mode, l, nxt - l, True, tr, tw, **kw)
+            l = nxt
+            if (l - 1) % stride == 0:
+                self.observer(prop_id, l - 1, direction, snaps)
+
     def _pad(self, rows, dtype=np.complex128):
         out = np.zeros((self.B, self.nt_max + 1), dtype)
         for b, r in enumerate(rows):
@@ -225,7 +250,10 @@ class GridBatch(_BatchBase):
     def run_prescribed(self):
         """single_pot / filtering / trans_wo_control / intuitive_control (fitter.py:425-438)."""
         self.goal_close_scal = np.zeros(self.B, np.complex128)
-        self.propagate(FORWARD)
+        pl = self.plan
+        pl.snapshot_load(0)
+        pl.set_E_base(self._pad([self._prescribed_field(p, FORWARD) for p in self.pbs]))
+        self._sweep("iter_0f", FORWARD, (0, 1), 0, eng.FIELD_PRESCRIBED, 1, self.nt_max, -1, -1)
         E0s = [self._prescribed_field(p, FORWARD)[0] for p in self.pbs]
         rows, _ = self._finish_forward(0, E0s)
         return [[r] for r in rows]
@@ -246,10 +274,10 @@ class GridBatch(_BatchBase):
             pl.record_state(0, 0, 0)                      # psi_tlist[0] = psi_init (fitter.py:227-229)
             if it == 0:
                 pl.set_E_base(self._pad([self._prescribed_field(p, FORWARD) for p in self.pbs]))
-                pl.sweep(0, eng.FIELD_PRESCRIBED, 1, self.nt_max, True, -1, 0)
+                self._sweep("iter_0f", FORWARD, (0, 1), 0, eng.FIELD_PRESCRIBED, 1, self.nt_max, -1, 0)
                 E0s = E_start
             else:
-                pl.sweep(0, eng.FIELD_KROTOV_FWD, 0, self.nt_max + 1, True, 1, 0)
+                self._sweep("iter_%df" % it, FORWARD, (0, 1), 0, eng.FIELD_KROTOV_FWD, 0, self.nt_max + 1, 1, 0)
                 E0s = None
             if E0s is None:
                 E0s = pl.get_fields()[:, 0]
@@ -273,7 +301,8 @@ class GridBatch(_BatchBase):
             if stop_all:
                 break
             pl.krotov_terminal(1, sqrt_hf_T, 1)
-            pl.sweep(1, eng.FIELD_KROTOV_BWD, 1, self.nt_max, True, 0, 1)
+            pl.snapshot_set(2)                            # chi(T): the "psi0" of the backward solver (fitter.py:247)
+            self._sweep("iter_%db" % it, BACKWARD, (2, 0), 1, eng.FIELD_KROTOV_BWD, 1, self.nt_max, 0, 1)
             it += 1
         return hist
 
@@ -302,7 +331,7 @@ class NLevelBatch(_BatchBase):
         rows = self._field_rows(FORWARD)
         pl.set_E_base(self._pad(rows))
         pl.snapshot_load(0)
-        pl.sweep(0, eng.FIELD_PRESCRIBED, 1, self.nt_max, True, -1, -1)
+        self._sweep("iter_0f", FORWARD, (0, 1), 0, eng.FIELD_PRESCRIBED, 1, self.nt_max, -1, -1)
         E = pl.get_fields()
         gc = pl.goal_overlap(1)
         out = []
@@ -366,9 +395,10 @@ class NLevelBatch(_BatchBase):
             if it == 0:
                 pl.set_control(1.0, self.nt.astype(np.float64))
                 pl.set_E_base(self._pad(self._field_rows(BACKWARD)))
-                pl.sweep(1, eng.FIELD_PRESCRIBED, 1, self.nt_max, True, -1, 1)
+                self._sweep("iter_0b", BACKWARD, (1, 0), 1, eng.FIELD_PRESCRIBED, 1, self.nt_max, -1, 1)
             else:
-                pl.sweep(1, eng.FIELD_PRESCRIBED, 1, self.nt_max, True, -1, 1, reversed_E=True)
+                self._sweep("iter_%db" % it, BACKWARD, (1, 0), 1, eng.FIELD_PRESCRIBED, 1, self.nt_max, -1, 1,
+                            reversed_E=True)
             chi_init = pl.get_state()
             # ---- l == 0 of the forward sweep: h_lambda and a0 (fitter.py:712-737) -------------------
             for b, p in enumerate(self.pbs):
@@ -382,7 +412,8 @@ class NLevelBatch(_BatchBase):
             if it == 0:
                 pl.set_E_base(self._pad(base_rows))
             pl.snapshot_load(0)
-            pl.sweep(0, eng.FIELD_UT_FWD, 0, self.nt_max + 1, True, 1, -1, write_E_base=True)
+            self._sweep("iter_%df" % it, FORWARD, (0, 1), 0, eng.FIELD_UT_FWD, 0, self.nt_max + 1, 1, -1,
+                        write_E_base=True)
             E = pl.get_fields()
             gc = pl.goal_overlap(1)
             stop_all = True

@@ -89,7 +89,9 @@ struct qc_plan {
     DevBuf<double> v, kin, uwd, dx, ctl, norms;
     int v_batched = 0, uwd_batched = 0, dx_batched = 0, expL_batched[2] = {0, 0}, s_batched = 0, ctl_batched = 0;
     bool static_set = false, ctl_set = false;
-    PolySlot poly[2];
+    PolySlot poly[3];                 // slot 2: internal identity polynomial (one bare H application)
+    DevBuf<cd> work[4];               // psi backup, H psi, T psi, P psi (instrumentation)
+    DevBuf<double> zero_v, akx, xgrid, instr;
 };
 
 // ---------------------------------------------------------------------------
@@ -194,6 +196,79 @@ __global__ void gather_nlevel_kernel(const cd *traj_slice, cd *out, int nb, int 
     const int run = (int)(gt / nbp), v = (int)(gt % nbp);
     if (v >= nb) return;
     for (int n = 0; n < nl; ++n) out[((long long)run * nb + v) * nl + n] = traj_slice[(long long)n * nthreads + gt];
+}
+
+
+// Per (run, vector, level) reductions of PropagationSolver.step's instrumentation block
+// (propagation.py:462-470, 260-299; phys_base.py:196-288).  out[item][20]:
+//  0,1 cnorm   2,3 cener   4,5 overlp0   6,7 overlpf   8,9 <x>   10,11 <x^2>   12,13 <p>   14,15 <p^2>
+//  16 max|psi|   17 Re psi at argmax|Re psi|   18,19 cprod(psi_0, psi_1) (sigma moments, written for level 0)
+__global__ void instrument_kernel(const cd *psi, const cd *hpsi, const cd *tpsi, const cd *ppsi, const cd *psi0,
+                                  const cd *psif, const double *x, const double *dx, int dx_stride, double two_m,
+                                  int nb, int nl, int np, double *out) {
+    const int item = blockIdx.x;                 // (run*nb + v)*nl + n
+    const int n = item % nl, run = item / (nl * nb);
+    const long long off = (long long)item * np;
+    const cd *a = psi + off;
+    double acc[16];
+    for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+    double mabs = 0.0, mre_abs = -1.0, mre = 0.0;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) {
+        const cd p = a[i];
+        const double w = p.x * p.x + p.y * p.y;
+        acc[0] += w;
+        if (hpsi) { const cd h = hpsi[off + i]; acc[2] += h.x * p.x + h.y * p.y; acc[3] += h.x * p.y - h.y * p.x; }
+        if (psi0) { const cd g = psi0[off + i]; acc[4] += p.x * g.x + p.y * g.y; acc[5] += p.x * g.y - p.y * g.x; }
+        if (psif) { const cd g = psif[off + i]; acc[6] += p.x * g.x + p.y * g.y; acc[7] += p.x * g.y - p.y * g.x; }
+        const double xi = x ? x[i] : 0.0;
+        acc[8] += w * xi;
+        acc[10] += w * xi * xi;
+        if (ppsi) { const cd h = ppsi[off + i]; acc[12] += h.x * p.x + h.y * p.y; acc[13] += h.x * p.y - h.y * p.x; }
+        if (tpsi) { const cd h = qc::cmk(tpsi[off + i].x * two_m, tpsi[off + i].y * two_m);
+                    acc[14] += h.x * p.x + h.y * p.y; acc[15] += h.x * p.y - h.y * p.x; }
+        if (n == 0 && nl == 2) { const cd q = a[np + i]; acc[1] += q.x * p.x + q.y * p.y; acc[9] += q.x * p.y - q.y * p.x; }
+        const double ab = sqrt(w);
+        if (ab > mabs) mabs = ab;
+        if (fabs(p.x) > mre_abs) { mre_abs = fabs(p.x); mre = p.x; }
+    }
+    __shared__ double red[16][32];
+    __shared__ double rmax[3][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) / 32;
+    for (int k = 0; k < 16; ++k) {
+        double v = acc[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[k][wid] = v;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double oa = __shfl_xor_sync(0xffffffffu, mabs, o);
+        const double ora = __shfl_xor_sync(0xffffffffu, mre_abs, o);
+        const double orv = __shfl_xor_sync(0xffffffffu, mre, o);
+        if (oa > mabs) mabs = oa;
+        if (ora > mre_abs) { mre_abs = ora; mre = orv; }
+    }
+    if (lane == 0) { rmax[0][wid] = mabs; rmax[1][wid] = mre_abs; rmax[2][wid] = mre; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double h = dx[(long long)dx_stride * run];
+        double t[16];
+        for (int k = 0; k < 16; ++k) { t[k] = 0.0; for (int w = 0; w < nw; ++w) t[k] += red[k][w]; }
+        double ma = 0.0, mra = -1.0, mr = 0.0;
+        for (int w = 0; w < nw; ++w) {
+            if (rmax[0][w] > ma) ma = rmax[0][w];
+            if (rmax[1][w] > mra) { mra = rmax[1][w]; mr = rmax[2][w]; }
+        }
+        double *o = out + (long long)item * 20;
+        o[0] = t[0] * h;  o[1] = 0.0;
+        o[2] = t[2] * h;  o[3] = t[3] * h;
+        o[4] = t[4] * h;  o[5] = t[5] * h;
+        o[6] = t[6] * h;  o[7] = t[7] * h;
+        o[8] = t[8] * h;  o[9] = 0.0;
+        o[10] = t[10] * h; o[11] = 0.0;
+        o[12] = t[12] * h; o[13] = t[13] * h;
+        o[14] = t[14] * h; o[15] = t[15] * h;
+        o[16] = ma; o[17] = mr;
+        o[18] = t[1] * h; o[19] = t[9] * h;
+    }
 }
 
 // FP64 FMA throughput: 8 independent chains per thread
@@ -462,6 +537,8 @@ extern "C" int32_t qc_plan_destroy(qc_plan *pl) {
     pl->gc.release(); pl->tmp_row.release(); for (auto &b : pl->snap) b.release(); pl->traj[0].release(); pl->traj[1].release();
     pl->v.release(); pl->kin.release(); pl->uwd.release(); pl->dx.release(); pl->ctl.release(); pl->norms.release();
     for (auto &s : pl->poly) { s.xp.release(); s.sc.release(); s.dv.release(); }
+    for (auto &b : pl->work) b.release();
+    pl->zero_v.release(); pl->akx.release(); pl->xgrid.release(); pl->instr.release();
     delete pl;
     return QC_OK;
 }
@@ -591,11 +668,18 @@ static int32_t launch_nlevel(qc_plan *pl, const qc::NLevelParams &np_) {
     return QC_OK;
 }
 
-static int32_t run_sweep(qc_plan *pl, const qc_sweep_args *a, bool single_step) {
+struct ApplyOpts {
+    bool active = false;        // bare operator application through the identity polynomial (slot 2)
+    bool cplx = false;          // complex coupling (orig=True form)
+    const double *v = nullptr;  // potential override (device) or null
+    const double *kin = nullptr;
+};
+
+static int32_t run_sweep(qc_plan *pl, const qc_sweep_args *a, bool single_step, const ApplyOpts &ap = ApplyOpts()) {
     if (!pl || !a) return fail(QC_ERR_ARG, "qc_sweep: NULL argument");
     const qc_plan_desc &d = pl->d;
     if (!pl->static_set) return fail(QC_ERR_STATE, "qc_sweep: qc_set_static has not been called");
-    if (a->poly_slot < 0 || a->poly_slot > 1 || !pl->poly[a->poly_slot].set)
+    if (a->poly_slot < 0 || a->poly_slot > (ap.active ? 2 : 1) || !pl->poly[a->poly_slot].set)
         return fail(QC_ERR_STATE, "qc_sweep: polynomial slot %d has not been set", a->poly_slot);
     if (a->nsteps < 1 || a->l_first < 0 || a->l_first > d.nt_max)
         return fail(QC_ERR_ARG, "qc_sweep: l_first=%d nsteps=%d (nt_max=%d)", a->l_first, a->nsteps, d.nt_max);
@@ -610,18 +694,19 @@ static int32_t run_sweep(qc_plan *pl, const qc_sweep_args *a, bool single_step) 
         return fail(QC_ERR_STATE, "qc_sweep: plan was created without trajectory buffers");
     if (mode != QC_FIELD_PRESCRIBED && a->traj_read < 0)
         return fail(QC_ERR_ARG, "qc_sweep: field mode %d reads the previous sweep; traj_read must be 0 or 1", mode);
-    if (d.hf_hide && !single_step && !pl->expL[a->poly_slot < 0 || a->poly_slot > 1 ? 0 : a->poly_slot].p) return fail(QC_ERR_STATE, "qc_sweep: exp_L table (qc_set_step_scalars which=1) missing");
+    if (d.hf_hide && !single_step && !pl->expL[a->poly_slot].p) return fail(QC_ERR_STATE, "qc_sweep: exp_L table (qc_set_step_scalars which=1) missing");
     if (mode == QC_FIELD_UT_FWD && !pl->s_env.p) return fail(QC_ERR_STATE, "qc_sweep: s_env table (qc_set_step_scalars which=2) missing");
     QC_CUDA(cudaSetDevice(pl->ctx->device));
     const PolySlot &ps = pl->poly[a->poly_slot];
     if (pl->grid) {
         qc::GridParams g;
         memset(&g, 0, sizeof g);
-        g.batch = d.batch; g.nch = d.nch; g.nt_max = d.nt_max;
+        g.batch = d.batch; g.nch = ap.active ? 2 : d.nch; g.nt_max = d.nt_max; g.cplx_coupling = ap.cplx ? 1 : 0;
         g.hf_hide = single_step ? 0 : d.hf_hide; g.renorm = a->renorm; g.field_mode = mode;
         g.reversed_E = a->reversed_E; g.write_E_base = a->write_E_base;
         g.l_first = a->l_first; g.nsteps = a->nsteps; g.single_step = single_step ? 1 : 0;
-        g.psi = pl->psi.p; g.v = pl->v.p; g.v_stride = pl->v_batched ? 2LL * d.np : 0; g.kin = pl->kin.p;
+        g.psi = pl->psi.p; g.v = ap.v ? ap.v : pl->v.p; g.v_stride = (!ap.v && pl->v_batched) ? 2LL * d.np : 0;
+        g.kin = ap.kin ? ap.kin : pl->kin.p;
         g.tw1 = pl->tw1.p; g.tw2 = pl->tw2.p; g.xp = ps.xp.p; g.dv = ps.dv.p; g.sc = ps.sc.p;
         g.poly_stride = ps.batched; g.dx = pl->dx.p; g.dx_stride = pl->dx_batched;
         g.E_base = pl->E_base.p; g.E_stride = 1; g.expL = pl->expL[a->poly_slot].p; g.expL_stride = pl->expL_batched[a->poly_slot];
@@ -639,7 +724,7 @@ static int32_t run_sweep(qc_plan *pl, const qc_sweep_args *a, bool single_step) 
     }
     qc::NLevelParams n;
     memset(&n, 0, sizeof n);
-    n.batch = d.batch; n.nb = d.nb; n.nbp = pl->nbp; n.nch = d.nch; n.nt_max = d.nt_max; n.hamil = d.hamil;
+    n.batch = d.batch; n.nb = d.nb; n.nbp = pl->nbp; n.nch = ap.active ? 2 : d.nch; n.nt_max = d.nt_max; n.hamil = d.hamil;
     n.renorm = a->renorm; n.field_mode = mode; n.reversed_E = a->reversed_E; n.write_E_base = a->write_E_base;
     n.l_first = a->l_first; n.nsteps = a->nsteps; n.single_step = single_step ? 1 : 0; n.nthreads = pl->nthreads;
     n.psi = pl->psi.p; n.vdiag = pl->v.p; n.v_stride = pl->v_batched; n.uwd = pl->uwd.p; n.uwd_stride = pl->uwd_batched;
@@ -674,6 +759,114 @@ extern "C" int32_t qc_prop_step(qc_plan *pl, int32_t poly_slot, const double *E)
     int32_t rc = run_sweep(pl, &a, true);
     if (rc) return rc;
     QC_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+    return QC_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// bare operator applications and instrumentation
+// ---------------------------------------------------------------------------
+static int32_t ensure_identity_poly(qc_plan *pl, double eL) {
+    PolySlot &s = pl->poly[2];
+    const int nch = pl->d.nch;
+    std::vector<double> xp(nch, 0.0), dv(2 * (size_t)nch, 0.0);
+    dv[2] = 1.0;                                   // dv = (0, 1, 0, ...): psi_out = (Hn - 0) psi
+    const double sc[4] = {-2.0, 2.0, 0.0, eL};     // c1 = 1, c2 = 0, phase = 1
+    int32_t rc = upload(pl, s.xp, xp.data(), nch);
+    if (!rc) rc = upload(pl, s.dv, dv.data(), nch);
+    if (!rc) rc = upload(pl, s.sc, sc, 4);
+    s.batched = 0;
+    s.set = rc == QC_OK;
+    return rc;
+}
+
+// psi <- Op psi on the device (the caller has saved psi if it needs it)
+static int32_t apply_operator(qc_plan *pl, int32_t which, int32_t orig, const double *E_host, double eL) {
+    const qc_plan_desc &d = pl->d;
+    cudaStream_t st = pl->ctx->stream;
+    int32_t rc = ensure_identity_poly(pl, (which == 0 && !orig) ? eL : 0.0);
+    if (rc) return rc;
+    if (which == 0 && E_host) {
+        QC_CUDA(cudaMemcpyAsync(pl->E_step.p, E_host, d.batch * sizeof(cd), cudaMemcpyHostToDevice, st));
+    } else {
+        QC_CUDA(cudaMemsetAsync(pl->E_step.p, 0, d.batch * sizeof(cd), st));
+    }
+    ApplyOpts ap;
+    ap.active = true;
+    ap.cplx = pl->grid && which == 0 && orig;
+    if (which != 0) {
+        if (!pl->grid) return fail(QC_ERR_ARG, "qc_apply_hamil: kinetic / momentum applications need a grid plan");
+        if (pl->zero_v.n != (size_t)2 * d.np) {
+            QC_CUDA(pl->zero_v.alloc((size_t)2 * d.np));
+            QC_CUDA(cudaMemsetAsync(pl->zero_v.p, 0, pl->zero_v.n * sizeof(double), st));
+        }
+        ap.v = pl->zero_v.p;
+        if (which == 2) {
+            if (!pl->akx.p) return fail(QC_ERR_STATE, "qc_apply_hamil: momentum multiplier not set (qc_set_instr_grid)");
+            ap.kin = pl->akx.p;
+        }
+    }
+    qc_sweep_args a;
+    memset(&a, 0, sizeof a);
+    a.poly_slot = 2; a.field_mode = QC_FIELD_PRESCRIBED; a.l_first = 1; a.nsteps = 1; a.renorm = 0;
+    a.traj_read = -1; a.traj_write = -1;
+    return run_sweep(pl, &a, true, ap);
+}
+
+extern "C" int32_t qc_apply_hamil(qc_plan *pl, int32_t which, int32_t orig, const double *E, double eL, double *out) {
+    if (!pl || !out) return fail(QC_ERR_ARG, "qc_apply_hamil: NULL argument");
+    if (which < 0 || which > 2) return fail(QC_ERR_ARG, "qc_apply_hamil: which=%d", which);
+    if (!pl->static_set) return fail(QC_ERR_STATE, "qc_apply_hamil: qc_set_static has not been called");
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    cudaStream_t st = pl->ctx->stream;
+    if (pl->work[0].n != pl->state_elems) QC_CUDA(pl->work[0].alloc(pl->state_elems));
+    const size_t bytes = pl->state_elems * sizeof(cd);
+    QC_CUDA(cudaMemcpyAsync(pl->work[0].p, pl->psi.p, bytes, cudaMemcpyDeviceToDevice, st));
+    int32_t rc = apply_operator(pl, which, orig, E, eL);
+    if (rc) return rc;
+    QC_CUDA(cudaMemcpyAsync(out, pl->psi.p, bytes, cudaMemcpyDeviceToHost, st));
+    QC_CUDA(cudaMemcpyAsync(pl->psi.p, pl->work[0].p, bytes, cudaMemcpyDeviceToDevice, st));
+    QC_CUDA(cudaStreamSynchronize(st));
+    return QC_OK;
+}
+
+extern "C" int32_t qc_set_instr_grid(qc_plan *pl, const double *x, const double *akx_re) {
+    if (!pl || !x) return fail(QC_ERR_ARG, "qc_set_instr_grid: NULL argument");
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    int32_t rc = upload(pl, pl->xgrid, x, pl->d.np);
+    if (!rc && akx_re) rc = upload(pl, pl->akx, akx_re, pl->d.np);
+    return rc;
+}
+
+extern "C" int32_t qc_instrument(qc_plan *pl, const double *E_full, double two_m, int32_t psi0_slot, int32_t psif_slot,
+                                 double *out) {
+    if (!pl || !out) return fail(QC_ERR_ARG, "qc_instrument: NULL argument");
+    if (!pl->static_set) return fail(QC_ERR_STATE, "qc_instrument: qc_set_static has not been called");
+    if (psi0_slot > 3 || psif_slot > 3) return fail(QC_ERR_ARG, "qc_instrument: snapshot slots");
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    const qc_plan_desc &d = pl->d;
+    cudaStream_t st = pl->ctx->stream;
+    const size_t bytes = pl->state_elems * sizeof(cd);
+    for (int k = 0; k < 4; ++k)
+        if (pl->work[k].n != pl->state_elems) QC_CUDA(pl->work[k].alloc(pl->state_elems));
+    QC_CUDA(cudaMemcpyAsync(pl->work[0].p, pl->psi.p, bytes, cudaMemcpyDeviceToDevice, st));
+    const bool moments = pl->grid && pl->akx.p;
+    for (int which = 0; which < (moments ? 3 : 1); ++which) {
+        int32_t rc = apply_operator(pl, which, 1, E_full, 0.0);
+        if (rc) return rc;
+        QC_CUDA(cudaMemcpyAsync(pl->work[1 + which].p, pl->psi.p, bytes, cudaMemcpyDeviceToDevice, st));
+        QC_CUDA(cudaMemcpyAsync(pl->psi.p, pl->work[0].p, bytes, cudaMemcpyDeviceToDevice, st));
+    }
+    const size_t items = (size_t)d.batch * d.nb * d.nlevs;
+    if (pl->instr.n != items * 20) QC_CUDA(pl->instr.alloc(items * 20));
+    instrument_kernel<<<(unsigned)items, d.np >= 256 ? 256 : 32, 0, st>>>(
+        pl->psi.p, pl->work[1].p, moments ? pl->work[2].p : nullptr, moments ? pl->work[3].p : nullptr,
+        psi0_slot >= 0 ? pl->snap[psi0_slot].p : nullptr, psif_slot >= 0 ? pl->snap[psif_slot].p : nullptr,
+        pl->xgrid.p, pl->dx.p, pl->dx_batched, two_m, d.nb, d.nlevs, d.np, pl->instr.p);
+    pl->ctx->launches++;
+    QC_CUDA(cudaGetLastError());
+    QC_CUDA(cudaMemcpyAsync(out, pl->instr.p, items * 20 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    QC_CUDA(cudaStreamSynchronize(st));
     return QC_OK;
 }
 

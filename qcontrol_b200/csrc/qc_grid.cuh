@@ -31,6 +31,7 @@ struct GridParams {
     int hf_hide, renorm, field_mode, reversed_E, write_E_base;
     int l_first, nsteps;
     int single_step;             // 1: qc_prop_step semantics (explicit E, no transform / renorm)
+    int cplx_coupling;           // 1 (single_step only): complex E_full, level 0 gets -E_full*psi_1, level 1 -conj(E_full)*psi_0
     cd *psi;                     // [batch][2][N]
     const double *v;             // [vb][2][N]
     long long v_stride;
@@ -221,8 +222,10 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
         }
         // ---- field of this step (fitter.py:650-811) --------------------------
         double E;
+        double Ei = 0.0;
         if (p.single_step) {
             E = p.E_step[run].x;
+            if (p.cplx_coupling) Ei = lev == 0 ? p.E_step[run].y : -p.E_step[run].y;
         } else if (p.field_mode == 0) {
             const int le = p.reversed_E ? (l == 0 ? nt : nt - l + 1) : l;
             E = p.E_base[erun + le].x;
@@ -248,6 +251,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
         }
         if (start_only) continue;
         const double cE = c1 * E;
+        const double cEi = c1 * Ei;
 
         // ---- Newton recurrence (phys_base.py:158-172) ------------------------
 #pragma unroll
@@ -320,6 +324,10 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
                     cd r;
                     r.x = fma(dd, own.x, fma(-cE, oth.x, a[n1].x));
                     r.y = fma(dd, own.y, fma(-cE, oth.y, a[n1].y));
+                    if (p.cplx_coupling) {           // orig=True form of hamil_2d.py:40-47 (uniform branch, off in sweeps)
+                        r.x = fma(cEi, oth.y, r.x);
+                        r.y = fma(-cEi, oth.x, r.y);
+                    }
                     a[n1] = r;
                     psi[n1] = cfma(dvj, r, psi[n1]);
                 }

@@ -237,3 +237,26 @@ class Plan:
 
     def record_state(self, buffer, index, level=0):
         check(lib.qc_record_state(self._h, int(buffer), int(index), int(level)))
+
+    # -- bare operator applications / instrumentation ------------------------------------------
+    def apply_hamil(self, which=0, orig=False, E=0.0, eL=0.0):
+        """phi = Op psi of the resident state (state unchanged): which 0 = H (orig or shifted form),
+        1 = kinetic operator, 2 = momentum operator."""
+        Ea = _c128(np.broadcast_to(np.asarray(E, np.complex128), (self.batch,)))
+        out = np.empty(self.state_shape, np.complex128)
+        check(lib.qc_apply_hamil(self._h, int(which), int(bool(orig)), _ptr(Ea.view(np.float64)), float(eL),
+                                 _ptr(out.view(np.float64))))
+        return out
+
+    def set_instr_grid(self, x, akx_re=None):
+        x = _f64(x, (self.np,))
+        k = _f64(akx_re, (self.np,)) if akx_re is not None else None
+        check(lib.qc_set_instr_grid(self._h, _ptr(x), _ptr(k)))
+
+    def instrument(self, E_full=0.0, two_m=1.0, psi0_slot=0, psif_slot=1):
+        """Device-side instrumentation table [batch][nb][nlevs][20] (see include/qcontrol_b200.h)."""
+        Ea = _c128(np.broadcast_to(np.asarray(E_full, np.complex128), (self.batch,)))
+        out = np.empty(self.state_shape[:3] + (20,), np.float64)
+        check(lib.qc_instrument(self._h, _ptr(Ea.view(np.float64)), float(two_m), int(psi0_slot), int(psif_slot),
+                                _ptr(out)))
+        return out

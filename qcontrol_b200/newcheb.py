@@ -1,0 +1,211 @@
+"""Batch entry point with the reference's command line (newcheb.py:612-979):
+
+    python -m qcontrol_b200.newcheb --json_task TASK.json --json_rep REPORT.json [--seed_base N]
+    torchrun --nproc-per-node 8 -m qcontrol_b200.newcheb --json_task ... --json_rep ...
+
+The task template is expanded over its "@SUBST:LIST" entries exactly like the reference does; instead of
+one thread-pool job (or SLURM job) per variant, variants that share a plan shape become ONE batched plan
+per GPU, the variants are split over the ranks by longest-processing-time-first, and each rank writes the
+iteration tables of its own runs (tab_iter.csv / tab_iter_E.csv, reporter.py:609-632) under the report's
+``out_path`` (with the reference's ``{input:$.json.path}`` templating).  Per-step tables and plots are the
+reference's I/O layer and are not reproduced here.
+"""
+from __future__ import annotations
+
+import copy
+import getopt
+import json
+import os
+import re
+import sys
+from types import SimpleNamespace
+
+import numpy
+
+from . import batch as qbatch
+from . import control, engine as _eng, task_manager
+from .config import TaskRootConfiguration
+
+_TT = TaskRootConfiguration.TaskType
+_NAMES = {_TT.SINGLE_POT: "single_pot", _TT.FILTERING: "filtering", _TT.TRANS_WO_CONTROL: "trans_wo_control",
+          _TT.INTUITIVE_CONTROL: "intuitive_control", _TT.OPTIMAL_CONTROL_KROTOV: "optimal_control_krotov",
+          _TT.OPTIMAL_CONTROL_UNIT_TRANSFORM: "optimal_control_unit_transform"}
+_HAMIL = {_eng.HAMIL_NONTRIV: "ntriv", _eng.HAMIL_TWO_LEVELS: "two_levels", _eng.HAMIL_BH_X: "bh_x",
+          _eng.HAMIL_BH_Z: "bh_z", _eng.HAMIL_QUBIT: "qubit"}
+
+
+def usage():
+    print("Usage: python -m qcontrol_b200.newcheb --json_task <task.json> --json_rep <report.json> [--json_create] "
+          "[--seed_base N]")
+
+
+def resolve_input_templates(data_task, node):
+    """Replace every "{input:$.a.b}" inside the report configuration by the value found at that path of
+    the task variant (newcheb.py:576-610; only plain dotted paths occur in the shipped files)."""
+    if isinstance(node, dict):
+        return {k: resolve_input_templates(data_task, v) for k, v in node.items()}
+    if isinstance(node, list):
+        return [resolve_input_templates(data_task, v) for v in node]
+    if isinstance(node, str):
+        def sub(m):
+            cur = data_task
+            for part in m.group(1).strip().lstrip("$").strip(".").split("."):
+                if part:
+                    cur = cur[part]
+            return str(cur)
+        return re.sub(r"\{input:([^\}]*)\}", sub, node)
+    return node
+
+
+def validate(conf):
+    """The subset of newcheb.py:691-902 that guards the supported task types."""
+    cp = conf.fitter.propagation
+    if not (conf.np > 0 and (conf.np & (conf.np - 1)) == 0):
+        raise ValueError("The number of collocation points 'np' must be a positive integer power of 2")
+    if not (cp.nch > 0 and (cp.nch & (cp.nch - 1)) == 0):
+        raise ValueError("The number of interpolation points 'nch' must be a positive integer power of 2")
+    if not conf.T > 0.0 or not conf.L > 0.0:
+        raise ValueError("'T' and 'L' must be positive")
+    if conf.task_type == _TT.OPTIMAL_CONTROL_UNIT_TRANSFORM:
+        if conf.np > 1:
+            raise ValueError("For the 'task_type' = 'optimal_control_unit_transform' the number of collocation points, "
+                             "'np', has to be equal to 1")
+        if conf.init_guess == TaskRootConfiguration.FitterConfiguration.InitGuess.ZERO:
+            raise ValueError("For the 'task_type' = 'optimal_control_unit_transform' the initial guess type for the "
+                             "laser field envelope, 'init_guess', mustn't be 'zero'")
+        if conf.L != 1.0:
+            raise ValueError("For the 'task_type' = 'optimal_control_unit_transform' the spatial range of the problem, "
+                             "'L', has to be equal to 1.0")
+    if conf.task_type not in _NAMES:
+        raise NotImplementedError("task type %s is not ported to the GPU path yet" % conf.task_type)
+
+
+def problem_from(conf, tm):
+    """Dense run description for the batched control loops from a task manager's products."""
+    cf, cp = conf.fitter, conf.fitter.propagation
+    h = tm.hamil2D
+    F = TaskRootConfiguration.FitterConfiguration
+    return SimpleNamespace(
+        task_type=_NAMES[conf.task_type], hamil=_HAMIL[h.kind], ntriv=tm.ntriv, np_=conf.np, nlevs=conf.nlevs,
+        nb=conf.nb, L=conf.L, T=conf.T, dx=tm.dx, x=tm.x, v=h.potentials(), vmin=h.minima(), akx2=tm.akx2,
+        psi0=tm.psi0.as_array(), psif=tm.psif.as_array(), U=conf.U, W=conf.W, delta=conf.delta, m=cp.m, nch=cp.nch,
+        nt=cp.nt, E0=cp.E0, t0=cp.t0, sigma=cp.sigma, nu_L=cp.nu_L, pcos=cf.pcos, w_list=cf.w_list,
+        hf_hide=bool(cf.hf_hide), h_lambda=cf.h_lambda, h_lambda_mode=cf.h_lambda_mode.name.lower(), epsilon=cf.epsilon,
+        iter_max=cf.iter_max, iter_mid_1=cf.iter_mid_1, iter_mid_2=cf.iter_mid_2, q=cf.q,
+        impulses_number=cf.impulses_number, delay=cf.delay,
+        F_type={F.FType.SM: "sm", F.FType.RE: "re", F.FType.SS: "ss"}[cf.F_type], F_goal=tm.F_goal, t_step=tm.t_step,
+        t_list=tm.t_list, laser_field=tm.laser_field, laser_field_hf=tm.laser_field_hf)
+
+
+def write_tables(out_path, rows, t_list, nt, imin=-1):
+    """tab_iter.csv / tab_iter_E.csv in the reference's format (reporter.py:609-632)."""
+    os.makedirs(out_path, exist_ok=True)
+    with open(os.path.join(out_path, "tab_iter.csv"), "w") as f, open(os.path.join(out_path, "tab_iter_E.csv"), "w") as g:
+        for r in rows:
+            if r.it < imin:
+                continue
+            f.write("{:2d} {:.6f} {:.6f} {:.4f} {:.6f}\n".format(int(r.it), r.goal_close, r.Fsm, r.E_int, r.J))
+            for i in range(nt + 1):
+                g.write("{:2d} {:.6f} {:.6e}\n".format(r.it, t_list[i] * 1e+15, abs(r.E_tlist[i])))
+
+
+def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True):
+    """Expand -> configure -> shard -> batched GPU runs -> per-run tables.  Returns {run index: rows}."""
+    import contextlib
+    import io
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0")) if device is None else device
+    confs, costs, shapes = [], [], []
+    for i, data_task in enumerate(variants):
+        with contextlib.redirect_stdout(io.StringIO()):
+            conf = TaskRootConfiguration()
+            conf.load(data_task)
+        validate(conf)
+        qbatch.apply_auto_rules(conf, run_index=i, seed_base=seed_base)
+        confs.append(conf)
+        costs.append(qbatch.estimate_cost(conf))
+        shapes.append((conf.hamil_type, conf.lf_aug_type, conf.np, conf.nlevs, conf.nb, conf.fitter.propagation.nch,
+                       bool(conf.fitter.hf_hide), conf.task_type, float(conf.L), float(conf.fitter.propagation.m)))
+    mine = qbatch.lpt_shards(costs, world)[rank]
+    results = {}
+    ctx = _eng.Context(local)
+    for shape, idxs in qbatch.plan_groups(shapes, mine).items():
+        pbs = []
+        for i in idxs:
+            with contextlib.redirect_stdout(io.StringIO()):
+                tm = task_manager.create(confs[i])
+            pbs.append(problem_from(confs[i], tm))
+        grid = pbs[0].hamil == "ntriv"
+        b = (control.GridBatch if grid else control.NLevelBatch)(pbs, ctx=ctx)
+        tt = pbs[0].task_type
+        if tt == "optimal_control_krotov":
+            hist = b.run_krotov()
+        elif tt == "optimal_control_unit_transform":
+            hist = b.run_unit_transform()
+        else:
+            hist = b.run_prescribed()
+        errors = getattr(b, "errors", [""] * len(idxs))
+        for k, i in enumerate(idxs):
+            results[i] = hist[k]
+            rep = resolve_input_templates(variants[i], copy.deepcopy(data_rep))
+            out_path = rep.get("fitter", {}).get("out_path", "output")
+            write_tables(out_path, hist[k], pbs[k].t_list, pbs[k].nt, rep.get("fitter", {}).get("table.imin", -1))
+            if errors[k] and verbose:
+                print("An exception interrupted the job #%d: %s" % (i, errors[k]), file=sys.stderr)
+            elif verbose:
+                print("Job #%d is done" % i)
+        b.close()
+    ctx.close()
+    return results
+
+
+def main(argv):
+    try:
+        opts, _ = getopt.getopt(argv, "h", ["help", "json_task=", "json_rep=", "json_create", "seed_base="])
+    except getopt.GetoptError:
+        usage()
+        return 2
+    file_task = file_rep = None
+    seed_base = 1000
+    for o, a in opts:
+        if o in ("-h", "--help"):
+            usage()
+            return 0
+        if o == "--json_task":
+            file_task = a
+        elif o == "--json_rep":
+            file_rep = a
+        elif o == "--seed_base":
+            seed_base = int(a)
+    if not file_task or not file_rep:
+        usage()
+        return 2
+    with open(file_task) as f:
+        data_task = json.load(f)
+    with open(file_rep) as f:
+        data_rep = json.load(f)
+    variants = qbatch.expand_substitutions(data_task)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+    results = run_variants(variants, data_rep, seed_base)
+    # the one collective of the path: every rank learns the final row of every run
+    local = {i: numpy.array([rows[-1].it, rows[-1].goal_close, rows[-1].Fsm, rows[-1].E_int, rows[-1].J])
+             for i, rows in results.items() if rows}
+    table = qbatch.gather_results(local, len(variants), 5)
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("run  iter  goal_close        Fsm            E_int          J")
+        for i, row in enumerate(table):
+            print("%4d %5.0f %12.6f %14.6f %14.4f %14.6f" % ((i,) + tuple(row)))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main(sys.argv[1:]))
