@@ -107,6 +107,85 @@ def step_times(pb, direction):
     return [t0] + [dt * l + t0 for l in range(1, nt + 1)]
 
 
+# Vectorised envelope / carrier evaluation for LARGE batches.  The scalar callables of a problem
+# (task_manager.py:18-159, Python ``math``) stay the source of truth and are used whenever the batch is
+# small enough (every parity test); beyond VECTOR_SETUP_POINTS table entries the same formulas are
+# evaluated with numpy over the whole time grid, which may differ from libm in the last ulp.
+VECTOR_SETUP_POINTS = 200000
+
+
+def _env_vec(name, E0, t, t0, sigma):
+    if name == "zero":
+        return np.zeros_like(t)
+    if name == "const":
+        return np.full_like(t, E0)
+    if name == "gauss":
+        return E0 * np.exp(-(t - t0) * (t - t0) / 2.0 / sigma / sigma)
+    if name == "sqrsin":
+        s = np.sin(2.0 * math.pi * (t - t0) / sigma)
+        return E0 * s * s
+    if name == "maxwell":
+        return E0 * t * t * np.exp(-(t - t0) * (t - t0) / 2.0 / sigma / sigma) / sigma / sigma
+    raise KeyError(name)
+
+
+def _hf_vec(name, nu, t, pcos, w):
+    base = 2.0 * math.pi * nu * 1.0 * t
+    if name == "exp":
+        return np.exp(1j * base)
+    if name == "cos":
+        return np.cos(base * pcos).astype(np.complex128)
+    if name == "sin":
+        return np.sin(base * pcos).astype(np.complex128)
+    if name == "cos_set":
+        acc = w[0] * np.cos(base)
+        k = -1
+        for q in range(2, math.floor(pcos) + 1):
+            k += 2
+            acc = acc + w[k] * np.cos(base * q) + w[k + 1] * np.cos(base / q)
+        return acc.astype(np.complex128)
+    if name == "sin_set":
+        acc = w[0] * np.sin(base)
+        for q in range(1, math.floor(pcos) + 1):
+            acc = acc + w[q] * np.sin(base * (2 * q + 1))
+        return acc.astype(np.complex128)
+    raise KeyError(name)
+
+
+def field_tables(p, direction, half_step=False, vectorised=False):
+    """(envelope[l], carrier[l]) for l = 0..nt at t_l (or t_l - |dt|/2 for l >= 1 when half_step)."""
+    ts = step_times(p, direction)
+    if vectorised and getattr(p, "envelope", None) and getattr(p, "carrier", None):
+        t = np.array(ts, np.float64)
+        if half_step:
+            t[1:] = t[1:] - abs(p.t_step) / 2.0
+        return (np.asarray(_env_vec(p.envelope, p.E0, t, p.t0, p.sigma), np.float64),
+                _hf_vec(p.carrier, p.nu, t, p.pcos, p.w_list))
+    env, hf = [], []
+    for k, t in enumerate(ts):
+        th = t - (abs(p.t_step) / 2.0) if (half_step and k > 0) else t
+        env.append(p.laser_field(p.E0, th, p.t0, p.sigma))
+        hf.append(p.laser_field_hf(np.float64(1.0), th, p.pcos, p.w_list))
+    return np.array(env, np.float64), np.array(hf, np.complex128)
+
+
+def _shown_fields(Et):
+    """|E| where E is complex, Re E otherwise: the list handed to print_iter_point_fitter (fitter.py:479-484)."""
+    Et = np.asarray(Et, np.complex128)
+    return np.where(Et.imag != 0.0, np.abs(Et), Et.real)
+
+
+def field_integral(Et, t_step):
+    """E_int = sum_{l>=1} |E_l|^2 * dt[fs] (fitter.py:338-341)."""
+    Et = np.asarray(Et)
+    if Et.shape[0] <= 4096:
+        acc = np.float64(0.0)
+        for k in range(1, Et.shape[0]):
+            acc += Et[k] * Et[k].conjugate() * (t_step * 1e15)
+        return acc
+    return np.complex128(np.sum(Et[1:] * np.conjugate(Et[1:])) * (t_step * 1e15))
+
+
 class _BatchBase:
     def __init__(self, problems: Sequence, ctx: eng.Context = None, device: int = 0, store_traj=True):
         self.pbs = list(problems)
@@ -144,6 +223,8 @@ class _BatchBase:
         self.plan.set_poly(slot, xp, dvs, np.array(emins), np.array(emaxs), np.array(tscs), np.array(eLs))
         self._poly_dir[direction] = slot
 
+    time_sweeps = False  # accumulate CUDA-event time of the sweep launches in sweep_ms (synchronises)
+    sweep_ms = 0.0
     observer = None      # callable(prop_id, l, direction, snapshots) invoked at l = 0 and every `stride` steps
     stride = 1
 
@@ -153,7 +234,11 @@ class _BatchBase:
         keep every mod-th one, propagation.py:291-299; here only those steps cost a host round trip)."""
         pl = self.plan
         if self.observer is None:
+            if self.time_sweeps:
+                self.ctx.timer_start()
             pl.sweep(slot, mode, l_first, nsteps, True, tr, tw, **kw)
+            if self.time_sweeps:
+                self.sweep_ms += self.ctx.timer_stop()
             return
         end = l_first + nsteps
         l = l_first
@@ -236,14 +321,12 @@ class GridBatch(_BatchBase):
         rows = []
         for b, p in enumerate(self.pbs):
             Et = np.array([E0_start[b]] + [E[b, l] for l in range(1, p.nt + 1)])
-            E_int = np.float64(0.0)
-            for k in range(1, p.nt + 1):
-                E_int += Et[k] * Et[k].conjugate() * (p.t_step * 1e15)
+            E_int = field_integral(Et, p.t_step)
             F = _F_value(p.F_type, gc[b], p.nb)
             hl = p.h_lambda if p.task_type == "optimal_control_krotov" else np.float64(0.0)
             J = F.real - hl * hl * E_int.real
             self.goal_close_scal[b] += gc[b].sum()
-            E_list = np.array([abs(e) if e.imag else e.real for e in Et])
+            E_list = _shown_fields(Et)
             rows.append(IterRow(it, float(abs(self.goal_close_scal[b])), float(F.real), float(E_int.real), float(J), E_list))
         return rows, gc
 
@@ -314,14 +397,15 @@ class NLevelBatch(_BatchBase):
         uwd = np.array([[float(p.U), float(p.W), float(p.delta)] for p in self.pbs])
         self.plan.set_static(np.stack([p.v for p in self.pbs]), None, uwd, self.dx)
 
+    def _vectorised(self):
+        return int(self.nt.sum()) > VECTOR_SETUP_POINTS
+
     def _field_rows(self, direction, half_step=False):
         rows = []
+        vec = self._vectorised()
         for p in self.pbs:
-            r = []
-            for t in step_times(p, direction):
-                th = t - (abs(p.t_step) / 2.0) if half_step else t
-                r.append(p.laser_field(p.E0, th, p.t0, p.sigma) * p.laser_field_hf(np.float64(1.0), th, p.pcos, p.w_list))
-            rows.append(r)
+            env, hf = field_tables(p, direction, half_step, vec)
+            rows.append(env * hf)
         return rows
 
     def run_prescribed(self):
@@ -337,11 +421,9 @@ class NLevelBatch(_BatchBase):
         out = []
         for b, p in enumerate(self.pbs):
             Et = np.array([rows[b][0]] + [E[b, l] for l in range(1, p.nt + 1)])
-            E_int = np.float64(0.0)
-            for k in range(1, p.nt + 1):
-                E_int += Et[k] * Et[k].conjugate() * (p.t_step * 1e15)
+            E_int = field_integral(Et, p.t_step)
             F = _F_value(p.F_type, gc[b], p.nb)
-            E_list = np.array([abs(e) if e.imag else e.real for e in Et])
+            E_list = _shown_fields(Et)
             out.append([IterRow(0, float(abs(gc[b].sum())), float(F.real), float(E_int.real), float(F.real), E_list)])
         return out
 
@@ -355,11 +437,13 @@ class NLevelBatch(_BatchBase):
                 gc0[v] += np.vdot(p.psi0[v][n], p.psif[v][n]) * p.dx
             sc += gc0[v]
         F0 = _F_value(p.F_type, gc0, p.nb)
-        El = [(p.laser_field(p.E0, t, p.t0, p.sigma) * p.laser_field_hf(np.float64(1.0), t, p.pcos, p.w_list)).real
-              for t in p.t_list]
-        Ei = np.float64(0.0)
-        for k in range(len(El) - 1):
-            Ei += El[k + 1] * np.conjugate(El[k + 1]) * (p.t_step * 1e15)
+        if self._vectorised() and getattr(p, "envelope", None):
+            t = np.array(p.t_list, np.float64)
+            El = list((_env_vec(p.envelope, p.E0, t, p.t0, p.sigma) * _hf_vec(p.carrier, p.nu, t, p.pcos, p.w_list)).real)
+        else:
+            El = [(p.laser_field(p.E0, t, p.t0, p.sigma) * p.laser_field_hf(np.float64(1.0), t, p.pcos, p.w_list)).real
+                  for t in p.t_list]
+        Ei = field_integral(np.array([0.0] + list(El[1:])), p.t_step).real
         h0 = p.h_lambda * RED_PLANCK_H / CM_TO_ERG if p.ntriv == -1 else p.h_lambda
         return IterRow(-1, float(abs(sc)), float(F0.real), float(Ei), float(F0.real - h0 * h0 * Ei), np.array(El))
 
@@ -376,14 +460,13 @@ class NLevelBatch(_BatchBase):
         a0 = np.zeros((B, self.pbs[0].nb), np.complex128)
         s_rows = []
         base_rows = []
+        vec = self._vectorised()
         for p in self.pbs:
-            sr, br = [0.0], [p.laser_field(p.E0, np.float64(0.0), p.t0, p.sigma) *
-                             p.laser_field_hf(np.float64(1.0), np.float64(0.0), p.pcos, p.w_list)]
-            for t in step_times(p, FORWARD)[1:]:
-                th = t - (abs(p.t_step) / 2.0)
-                s = p.laser_field(p.E0, th, p.t0, p.sigma) / p.E0
-                sr.append(s)
-                br.append(s * p.E0 * p.laser_field_hf(np.float64(1.0), th, p.pcos, p.w_list))
+            env, hf = field_tables(p, FORWARD, True, vec)
+            sr = env / p.E0
+            sr[0] = 0.0
+            br = sr * p.E0 * hf                          # s * E0 * hf(t - |dt|/2)   (fitter.py:753-755)
+            br[0] = env[0] * hf[0]                       # E_patched at t = 0        (fitter.py:653-658)
             s_rows.append(sr)
             base_rows.append(br)
         pl.set_s_env(self._pad(s_rows))
@@ -421,13 +504,11 @@ class NLevelBatch(_BatchBase):
                 if done[b]:
                     continue
                 Et = E[b, :p.nt + 1]
-                E_int = np.float64(0.0)
-                for k in range(1, p.nt + 1):
-                    E_int += Et[k] * Et[k].conjugate() * (p.t_step * 1e15)
+                E_int = field_integral(Et, p.t_step)
                 F = _F_value(p.F_type, gc[b], p.nb)
                 J = F.real - h_lambda[b] * h_lambda[b] * E_int.real
                 goal_close_abs[b] = abs(gc[b].sum())
-                E_list = np.array([abs(e) if e.imag else e.real for e in Et])
+                E_list = _shown_fields(Et)
                 hist[b].append(IterRow(it, float(goal_close_abs[b]), float(F.real), float(E_int.real), float(J), E_list))
                 if p.q and it >= 1:                       # divergence guard (fitter.py:550-560)
                     if it == p.iter_mid_1:

@@ -94,7 +94,8 @@ def problem_from(conf, tm):
         iter_max=cf.iter_max, iter_mid_1=cf.iter_mid_1, iter_mid_2=cf.iter_mid_2, q=cf.q,
         impulses_number=cf.impulses_number, delay=cf.delay,
         F_type={F.FType.SM: "sm", F.FType.RE: "re", F.FType.SS: "ss"}[cf.F_type], F_goal=tm.F_goal, t_step=tm.t_step,
-        t_list=tm.t_list, laser_field=tm.laser_field, laser_field_hf=tm.laser_field_hf)
+        t_list=tm.t_list, laser_field=tm.laser_field, laser_field_hf=tm.laser_field_hf,
+        envelope=conf.init_guess.name.lower(), carrier=conf.init_guess_hf.name.lower(), nu=tm.nu)
 
 
 def write_tables(out_path, rows, t_list, nt, imin=-1):

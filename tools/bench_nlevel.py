@@ -51,8 +51,12 @@ def main():
         pbs.append(newcheb.problem_from(c, tm))
     for copies in a.copies:
         runs = pbs * copies
+        t0 = time.perf_counter()
         nb = control.NLevelBatch(runs, ctx=ctx)
+        nb.run_unit_transform(iter_max=0)            # set-up + one iteration (tables, uploads, first sweeps)
         ctx.synchronize()
+        setup_s = time.perf_counter() - t0
+        nb.time_sweeps, nb.sweep_ms = True, 0.0
         t0 = time.perf_counter()
         hist = nb.run_unit_transform()
         ctx.synchronize()
@@ -61,7 +65,7 @@ def main():
         steps = sum(p.nt for p in runs) * 2 * iters * runs[0].nb          # solver steps (per basis vector)
         traj_bytes = sum(p.nt for p in runs) * iters * 2 * runs[0].nb * runs[0].nlevs * 16
         print(json.dumps({"workload": "ut_jx_Tsweep x%d" % copies, "runs": len(runs), "iterations_per_run": iters,
-                          "wall_s": wall, "ut_iterations_per_s": len(runs) * iters / wall,
+                          "wall_s": wall, "sweep_kernels_s": nb.sweep_ms * 1e-3, "first_call_incl_setup_s": setup_s, "ut_iterations_per_s": len(runs) * iters / wall,
                           "solver_steps_per_s": steps / wall, "traj_hbm_gbs_algorithmic": traj_bytes / wall / 1e9,
                           "nt_range": [min(p.nt for p in runs), max(p.nt for p in runs)], "launches": ctx.launches}))
         nb.close()
