@@ -48,7 +48,17 @@ struct qc_context {
     bool owns_stream;
     cudaEvent_t ev0, ev1;
     long long launches;
+    int live_plans;      // plans that still point at this context
+    bool released;       // qc_destroy was called while plans were alive: freed with the last plan
 };
+
+static void context_free(qc_context *ctx) {
+    cudaSetDevice(ctx->device);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
 
 template <typename T>
 struct DevBuf {
@@ -372,6 +382,8 @@ extern "C" int32_t qc_create(int32_t device, void *stream, qc_context **out) {
     qc_context *c = new qc_context();
     c->device = device;
     c->launches = 0;
+    c->live_plans = 0;
+    c->released = false;
     if (stream) {
         c->stream = (cudaStream_t)stream;
         c->owns_stream = false;
@@ -387,11 +399,11 @@ extern "C" int32_t qc_create(int32_t device, void *stream, qc_context **out) {
 
 extern "C" int32_t qc_destroy(qc_context *ctx) {
     if (!ctx) return QC_OK;
-    cudaSetDevice(ctx->device);
-    cudaEventDestroy(ctx->ev0);
-    cudaEventDestroy(ctx->ev1);
-    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
-    delete ctx;
+    if (ctx->live_plans > 0) {       // plans outlive the handle: defer, never leave them a dangling pointer
+        ctx->released = true;
+        return QC_OK;
+    }
+    context_free(ctx);
     return QC_OK;
 }
 
@@ -475,6 +487,7 @@ extern "C" int32_t qc_plan_create(qc_context *ctx, const qc_plan_desc *desc, qc_
     QC_CUDA(cudaSetDevice(ctx->device));
     qc_plan *pl = new qc_plan();
     pl->ctx = ctx;
+    ctx->live_plans++;
     pl->d = d;
     pl->grid = grid;
     pl->log2n = grid ? ilog2(d.np) : 0;
@@ -539,7 +552,9 @@ extern "C" int32_t qc_plan_destroy(qc_plan *pl) {
     for (auto &s : pl->poly) { s.xp.release(); s.sc.release(); s.dv.release(); }
     for (auto &b : pl->work) b.release();
     pl->zero_v.release(); pl->akx.release(); pl->xgrid.release(); pl->instr.release();
+    qc_context *ctx = pl->ctx;
     delete pl;
+    if (--ctx->live_plans == 0 && ctx->released) context_free(ctx);
     return QC_OK;
 }
 

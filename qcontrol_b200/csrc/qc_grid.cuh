@@ -86,6 +86,47 @@ __device__ __forceinline__ void bar_arrive(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+#ifdef QC_TMEM
+// ---- Tensor memory as a per-thread scratchpad ------------------------------------------------------
+// The accumulator psi and the thread's own copy of phi live in TMEM between their uses: TMEM has its own
+// datapath (tcgen05.ld / tcgen05.st), so this traffic does not compete with the shared-memory pipe that
+// bounds the kernel, and it frees 64 registers (no spills, k-space multiplier back in registers).
+// Each thread owns one TMEM lane (warp w -> lanes 32*(w%4)..+31) and 128 columns: 64 for psi, 64 for phi.
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// four complex128 values <-> 16 TMEM columns
+__device__ __forceinline__ void tmem_store_c4(uint32_t taddr, const cd *v) {
+    uint32_t r[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        r[4 * i + 0] = (uint32_t)__double2loint(v[i].x);
+        r[4 * i + 1] = (uint32_t)__double2hiint(v[i].x);
+        r[4 * i + 2] = (uint32_t)__double2loint(v[i].y);
+        r[4 * i + 3] = (uint32_t)__double2hiint(v[i].y);
+    }
+    tmem_st16(taddr, r);
+}
+__device__ __forceinline__ void tmem_unpack_c4(const uint32_t (&r)[16], cd *v) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        v[i] = cmk(__hiloint2double((int)r[4 * i + 1], (int)r[4 * i + 0]), __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2]));
+}
+#endif
+
 // a[k] *= w^k (k = 1..15) with a running product; conjugated for the inverse transform
 template <bool INV>
 __device__ __forceinline__ void twiddle_powers(cd *a, const cd w) {
@@ -191,6 +232,25 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) psi[n1] = src[t + TPL * n1];
     }
+#ifdef QC_TMEM
+    // one warp allocates 128 columns per warp slot (warps w and w+4 share a lane quadrant)
+    constexpr int TM_COLS = C::NTHREADS > 128 ? 256 : 128;
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_red + 30);
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(s_tmem)),
+                     "n"(TM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *s_tmem;
+    const int warp = tid >> 5;
+    const uint32_t t_psi = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128);
+    const uint32_t t_phi = t_psi + 64;
+#endif
     __syncthreads();
 
     const cd *traj_in = p.traj_in ? p.traj_in + (long long)run * (p.nt_max + 1) * N : nullptr;
@@ -259,6 +319,10 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
             a[i] = psi[i];
             psi[i] = cmul(psi[i], s_dv[0]);
         }
+#ifdef QC_TMEM
+#pragma unroll
+        for (int c4 = 0; c4 < 16; c4 += 4) tmem_store_c4(t_psi + c4 * 4, psi + c4);
+#endif
         for (int j = 0; j <= last_j; ++j) {
             const double xpj = s_xp[j];
             const cd dvj = s_dv[j + 1];
@@ -268,6 +332,10 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
             if (NAMED && j > 0) bar_sync(BAR_REL_OWN, C::NTHREADS);
 #pragma unroll
             for (int n1 = 0; n1 < 16; ++n1) stash[t + TPL * n1] = a[n1];
+#ifdef QC_TMEM
+#pragma unroll
+            for (int c4 = 0; c4 < 16; c4 += 4) tmem_store_c4(t_phi + c4 * 4, a + c4);   // own copy, read back below
+#endif
             if (NAMED) bar_arrive(BAR_FULL_OWN, C::NTHREADS);   // producer side of a named barrier: no fence (FA3 pattern)
             // pass 1 : DFT over n1, twiddle w_N^(k1*t)
             dft16_twiddle_out<false>(a, w1, [&](int k1, cd val) { bufA[k1 * S1 + t] = val; });
@@ -314,6 +382,36 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
             if (NAMED) bar_sync(BAR_FULL_OTH, C::NTHREADS);
             // in chunks of four grid points: the compiler otherwise hoists all 32 shared loads above the
             // arithmetic and spills (the register file holds phi, psi and d with little to spare)
+#ifdef QC_TMEM
+            tmem_wait_st();
+#pragma unroll
+            for (int c4 = 0; c4 < 16; c4 += 4) {
+                uint32_t rp[16], rs[16];
+                tmem_ld16(t_psi + c4 * 4, rp);
+                tmem_ld16(t_phi + c4 * 4, rs);
+                cd oth4[4], own4[4], acc4[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) oth4[i] = stash_other[t + TPL * (c4 + i)];
+                tmem_wait_ld();
+                tmem_unpack_c4(rp, acc4);
+                tmem_unpack_c4(rs, own4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int n1 = c4 + i;
+                    const double dd = dcoef[n1] - xpj;
+                    cd r;
+                    r.x = fma(dd, own4[i].x, fma(-cE, oth4[i].x, a[n1].x));
+                    r.y = fma(dd, own4[i].y, fma(-cE, oth4[i].y, a[n1].y));
+                    if (p.cplx_coupling) {
+                        r.x = fma(cEi, oth4[i].y, r.x);
+                        r.y = fma(-cEi, oth4[i].x, r.y);
+                    }
+                    a[n1] = r;
+                    acc4[i] = cfma(dvj, r, acc4[i]);
+                }
+                tmem_store_c4(t_psi + c4 * 4, acc4);
+            }
+#else
 #pragma unroll
             for (int c4 = 0; c4 < 16; c4 += 4) {
 #pragma unroll
@@ -333,12 +431,23 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
                 }
                 asm volatile("" ::: "memory");
             }
+#endif
             if (NAMED) {
                 if (j < last_j) bar_arrive(BAR_REL_OTH, C::NTHREADS);
             } else {
                 __syncthreads();                                                   // (#3) stash reuse
             }
         }
+#ifdef QC_TMEM
+        tmem_wait_st();
+#pragma unroll
+        for (int c4 = 0; c4 < 16; c4 += 4) {
+            uint32_t rp[16];
+            tmem_ld16(t_psi + c4 * 4, rp);
+            tmem_wait_ld();
+            tmem_unpack_c4(rp, psi + c4);
+        }
+#endif
         // ---- final phase (phys_base.py:174-176), norms, renormalisation --------
         double nrm = 0.0;
 #pragma unroll
@@ -389,6 +498,13 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) dst[t + TPL * n1] = psi[n1];
     }
+#ifdef QC_TMEM
+    tmem_wait_st();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TM_COLS) : "memory");
+#endif
 }
 
 }  // namespace qc
