@@ -221,6 +221,61 @@ __device__ __forceinline__ void dft16_twiddle_in_inv(cd *a, const cd w, Source s
         }
 }
 
+// ---- the same two streamed transforms with the twiddles w^k taken from a per-thread table instead of a
+// ---- running product.  TwSrc::prefetch(g) starts fetching the four twiddles {w^g, w^(g+4), w^(g+8), w^(g+12)}
+// ---- of radix-4 group g, TwSrc::get(w4) waits for them (tensor-memory table, see qc_grid.cuh).
+template <bool INV, class TwSrc, class Sink>
+__device__ __forceinline__ void dft16_table_out(cd *a, TwSrc &tw, Sink sink) {
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) dft4<INV>(a[nb], a[4 + nb], a[8 + nb], a[12 + nb]);
+    dft16_internal_twiddles<INV>(a);
+#pragma unroll
+    for (int ka = 0; ka < 4; ++ka) {
+        tw.prefetch(ka);
+        dft4<INV>(a[4 * ka], a[4 * ka + 1], a[4 * ka + 2], a[4 * ka + 3]);   // X[ka + 4 kb] in a[4 ka + kb]
+        cd w4[4];
+        tw.get(w4);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+            if (ka == 0 && kb == 0)
+                sink(0, a[0]);
+            else
+                sink(ka + 4 * kb, cmul(a[4 * ka + kb], w4[kb]));
+        }
+    }
+}
+
+template <class TwSrc, class Source>
+__device__ __forceinline__ void dft16_table_in_inv(cd *a, TwSrc &tw, Source source) {
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+        tw.prefetch(nb);
+        cd x0 = source(nb), x1 = source(nb + 4), x2 = source(nb + 8), x3 = source(nb + 12);
+        cd w4[4];
+        tw.get(w4);
+        if (nb != 0) x0 = cmulc(x0, w4[0]);
+        x1 = cmulc(x1, w4[1]);
+        x2 = cmulc(x2, w4[2]);
+        x3 = cmulc(x3, w4[3]);
+        dft4<true>(x0, x1, x2, x3);
+        a[nb] = x0;
+        a[4 + nb] = x1;
+        a[8 + nb] = x2;
+        a[12 + nb] = x3;
+    }
+    dft16_internal_twiddles<true>(a);
+#pragma unroll
+    for (int ka = 0; ka < 4; ++ka) dft4<true>(a[4 * ka], a[4 * ka + 1], a[4 * ka + 2], a[4 * ka + 3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = i + 1; j < 4; ++j) {
+            cd t = a[4 * i + j];
+            a[4 * i + j] = a[4 * j + i];
+            a[4 * j + i] = t;
+        }
+}
+
 template <int R, bool INV>
 __device__ __forceinline__ void dft(cd *a) {
     if (R == 2) dft2<INV>(a[0], a[1]);

@@ -125,6 +125,30 @@ __device__ __forceinline__ void tmem_unpack_c4(const uint32_t (&r)[16], cd *v) {
     for (int i = 0; i < 4; ++i)
         v[i] = cmk(__hiloint2double((int)r[4 * i + 1], (int)r[4 * i + 0]), __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2]));
 }
+// per-thread twiddle table in TMEM: 16 complex values in radix-4 group order, T[4 g + h] = w^(g + 4 h)
+struct TmemTwiddles {
+    uint32_t taddr;
+    uint32_t r[16];
+    __device__ __forceinline__ explicit TmemTwiddles(uint32_t a) : taddr(a) {}
+    __device__ __forceinline__ void prefetch(int g) { tmem_ld16(taddr + 16 * g, r); }
+    __device__ __forceinline__ void get(cd *w4) {
+        tmem_wait_ld();
+        tmem_unpack_c4(r, w4);
+    }
+};
+// fill the table of one root: powers by repeated squaring / pairing (depth log2 k), stored group-major
+__device__ __forceinline__ void tmem_fill_twiddles(uint32_t taddr, const cd w) {
+    cd pw[16];
+    pw[0] = cmk(1.0, 0.0);
+    pw[1] = w;
+#pragma unroll
+    for (int k = 2; k < 16; ++k) pw[k] = cmul(pw[k / 2], pw[k - k / 2]);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        cd grp[4] = {pw[g], pw[g + 4], pw[g + 8], pw[g + 12]};
+        tmem_store_c4(taddr + 16 * g, grp);
+    }
+}
 #endif
 
 // a[k] *= w^k (k = 1..15) with a running product; conjugated for the inverse transform
@@ -234,7 +258,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
     }
 #ifdef QC_TMEM
     // one warp allocates 128 columns per warp slot (warps w and w+4 share a lane quadrant)
-    constexpr int TM_COLS = C::NTHREADS > 128 ? 256 : 128;
+    constexpr int TM_COLS = C::NTHREADS > 128 ? 512 : 256;     // 256 columns per warp slot: psi, phi, two twiddle tables
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_red + 30);
     if (tid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -248,8 +272,12 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *s_tmem;
     const int warp = tid >> 5;
-    const uint32_t t_psi = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128);
+    const uint32_t t_psi = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 256);
     const uint32_t t_phi = t_psi + 64;
+    const uint32_t t_tw1 = t_psi + 128, t_tw2 = t_psi + 192;
+    tmem_fill_twiddles(t_tw1, w1);
+    tmem_fill_twiddles(t_tw2, w2);
+    tmem_wait_st();
 #endif
     __syncthreads();
 
@@ -338,7 +366,14 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
 #endif
             if (NAMED) bar_arrive(BAR_FULL_OWN, C::NTHREADS);   // producer side of a named barrier: no fence (FA3 pattern)
             // pass 1 : DFT over n1, twiddle w_N^(k1*t)
+#ifdef QC_TMEM
+            {
+                TmemTwiddles tw(t_tw1);
+                dft16_table_out<false>(a, tw, [&](int k1, cd val) { bufA[k1 * S1 + t] = val; });
+            }
+#else
             dft16_twiddle_out<false>(a, w1, [&](int k1, cd val) { bufA[k1 * S1 + t] = val; });
+#endif
             if (NAMED) bar_sync(BAR_LEVEL, TPL); else __syncthreads();              // (#1)
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) a[n2] = bufA[k1p * S1 + n2 * R3 + n3p];
@@ -346,7 +381,14 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
             if (R3 == 1) dft16<false>(a);
             if (R3 > 1) {
                 __syncwarp();
+#ifdef QC_TMEM
+                {
+                    TmemTwiddles tw(t_tw2);
+                    dft16_table_out<false>(a, tw, [&](int k2, cd val) { bufA[k1p * S1 + pos2<R3, Q>(k2, n3p)] = val; });
+                }
+#else
                 dft16_twiddle_out<false>(a, w2, [&](int k2, cd val) { bufA[k1p * S1 + pos2<R3, Q>(k2, n3p)] = val; });
+#endif
                 __syncwarp();
 #pragma unroll
                 for (int e = 0; e < 16; ++e)
@@ -368,7 +410,14 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
                 for (int e = 0; e < 16; ++e)
                     bufB[k1p * S1 + pos2<R3, Q>(n3p * Q + e / R3, e % R3)] = a[e];
                 __syncwarp();
+#ifdef QC_TMEM
+                {
+                    TmemTwiddles tw(t_tw2);
+                    dft16_table_in_inv(a, tw, [&](int k2) { return bufB[k1p * S1 + pos2<R3, Q>(k2, n3p)]; });
+                }
+#else
                 dft16_twiddle_in_inv(a, w2, [&](int k2) { return bufB[k1p * S1 + pos2<R3, Q>(k2, n3p)]; });
+#endif
                 __syncwarp();
             }
             // inverse pass 2
@@ -377,7 +426,14 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
             for (int n2 = 0; n2 < 16; ++n2) bufB[k1p * S1 + n2 * R3 + n3p] = a[n2];
             if (NAMED) bar_sync(BAR_LEVEL, TPL); else __syncthreads();              // (#2)
             // inverse pass 1 -> kinetic term (already scaled by c1) at x = t + TPL*n1
+#ifdef QC_TMEM
+            {
+                TmemTwiddles tw(t_tw1);
+                dft16_table_in_inv(a, tw, [&](int k1) { return bufB[k1 * S1 + t]; });
+            }
+#else
             dft16_twiddle_in_inv(a, w1, [&](int k1) { return bufB[k1 * S1 + t]; });
+#endif
             // pointwise part (hamil_2d.py:60-71, phys_base.py:98-111) and accumulation (phys_base.py:170-172)
             if (NAMED) bar_sync(BAR_FULL_OTH, C::NTHREADS);
             // in chunks of four grid points: the compiler otherwise hoists all 32 shared loads above the
