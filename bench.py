@@ -248,7 +248,8 @@ def run_gpu_arm(a):
         e2e_s = float(np.min(e2e_t[1:]))
         e2e = {"value": B * NP_ * nt / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(hin.numel() * 16),
                "d2h_bytes_per_step": int(hout.numel() * 16),
-               "call": "qc_propagate_host: H2D psi (pinned) + %d prescribed-field steps + D2H psi, one GPU" % nt}
+               "call": "qc_propagate_host: H2D psi (pinned) + %d prescribed-field steps + D2H psi per GPU, "
+                       "copies pipelined against the propagation in chunks of 592 runs" % nt}
         # ---- CPU baseline beside it ---------------------------------------------------------------------
         cpu = None
         if not a.no_cpu:

@@ -47,6 +47,9 @@ struct qc_context {
     cudaStream_t stream;
     bool owns_stream;
     cudaEvent_t ev0, ev1;
+    cudaStream_t aux[2];     // extra streams for the chunked host pipeline of qc_propagate_host (lazy)
+    cudaEvent_t aux_ev[3];
+    bool aux_ready;
     long long launches;
     int live_plans;      // plans that still point at this context
     bool released;       // qc_destroy was called while plans were alive: freed with the last plan
@@ -57,6 +60,10 @@ static void context_free(qc_context *ctx) {
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->aux_ready) {
+        for (auto &a : ctx->aux) cudaStreamDestroy(a);
+        for (auto &e : ctx->aux_ev) cudaEventDestroy(e);
+    }
     delete ctx;
 }
 
@@ -383,6 +390,7 @@ extern "C" int32_t qc_create(int32_t device, void *stream, qc_context **out) {
     c->device = device;
     c->launches = 0;
     c->live_plans = 0;
+    c->aux_ready = false;
     c->released = false;
     if (stream) {
         c->stream = (cudaStream_t)stream;
@@ -658,7 +666,7 @@ extern "C" int32_t qc_set_control(qc_plan *pl, const double *ctl, int32_t batche
 // sweeps
 // ---------------------------------------------------------------------------
 template <int LOG2N>
-static int32_t launch_grid(qc_plan *pl, const qc::GridParams &gp) {
+static int32_t launch_grid(qc_plan *pl, const qc::GridParams &gp, cudaStream_t stream) {
     typedef qc::GridCfg<LOG2N> C;
     static bool attr_done[64] = {false};
     const int dev = pl->ctx->device;
@@ -667,7 +675,7 @@ static int32_t launch_grid(qc_plan *pl, const qc::GridParams &gp) {
                                      (int)C::SMEM_BYTES));
         attr_done[dev & 63] = true;
     }
-    qc::grid_sweep_kernel<LOG2N><<<gp.batch, C::NTHREADS, C::SMEM_BYTES, pl->ctx->stream>>>(gp);
+    qc::grid_sweep_kernel<LOG2N><<<gp.run_count, C::NTHREADS, C::SMEM_BYTES, stream>>>(gp);
     pl->ctx->launches++;
     QC_CUDA(cudaGetLastError());
     return QC_OK;
@@ -684,6 +692,8 @@ static int32_t launch_nlevel(qc_plan *pl, const qc::NLevelParams &np_) {
 }
 
 struct ApplyOpts {
+    int run_first = 0, run_count = -1;   // sub-range of the batch (grid plans), -1 = all
+    cudaStream_t stream = nullptr;       // launch stream override
     bool active = false;        // bare operator application through the identity polynomial (slot 2)
     bool cplx = false;          // complex coupling (orig=True form)
     const double *v = nullptr;  // potential override (device) or null
@@ -716,6 +726,8 @@ static int32_t run_sweep(qc_plan *pl, const qc_sweep_args *a, bool single_step, 
     if (pl->grid) {
         qc::GridParams g;
         memset(&g, 0, sizeof g);
+        g.run_first = ap.run_first; g.run_count = ap.run_count < 0 ? d.batch : ap.run_count;
+        cudaStream_t lst = ap.stream ? ap.stream : pl->ctx->stream;
         g.batch = d.batch; g.nch = ap.active ? 2 : d.nch; g.nt_max = d.nt_max; g.cplx_coupling = ap.cplx ? 1 : 0;
         g.hf_hide = single_step ? 0 : d.hf_hide; g.renorm = a->renorm; g.field_mode = mode;
         g.reversed_E = a->reversed_E; g.write_E_base = a->write_E_base;
@@ -730,10 +742,10 @@ static int32_t run_sweep(qc_plan *pl, const qc_sweep_args *a, bool single_step, 
         g.traj_out = a->traj_write >= 0 ? pl->traj[a->traj_write].p : nullptr;
         g.norms = pl->norms.p;
         switch (pl->log2n) {
-            case 8: return launch_grid<8>(pl, g);
-            case 9: return launch_grid<9>(pl, g);
-            case 10: return launch_grid<10>(pl, g);
-            case 11: return launch_grid<11>(pl, g);
+            case 8: return launch_grid<8>(pl, g, lst);
+            case 9: return launch_grid<9>(pl, g, lst);
+            case 10: return launch_grid<10>(pl, g, lst);
+            case 11: return launch_grid<11>(pl, g, lst);
         }
         return fail(QC_ERR_ARG, "qc_sweep: unsupported np");
     }
@@ -1013,11 +1025,50 @@ extern "C" int32_t qc_record_state(qc_plan *pl, int32_t buffer, int32_t index, i
 extern "C" int32_t qc_propagate_host(qc_plan *pl, const qc_sweep_args *args, const double *psi_in, double *psi_out) {
     if (!pl || !args || !psi_in || !psi_out) return fail(QC_ERR_ARG, "qc_propagate_host: NULL argument");
     QC_CUDA(cudaSetDevice(pl->ctx->device));
-    cudaStream_t st = pl->ctx->stream;
-    QC_CUDA(cudaMemcpyAsync(pl->psi.p, psi_in, pl->state_elems * sizeof(cd), cudaMemcpyHostToDevice, st));
-    int32_t rc = run_sweep(pl, args, false);
-    if (rc) return rc;
-    QC_CUDA(cudaMemcpyAsync(psi_out, pl->psi.p, pl->state_elems * sizeof(cd), cudaMemcpyDeviceToHost, st));
+    qc_context *ctx = pl->ctx;
+    cudaStream_t st = ctx->stream;
+    const qc_plan_desc &d = pl->d;
+    const int chunk = 592;                                   // 4 waves of 148 CTAs
+    if (!pl->grid || d.batch <= chunk || args->field_mode != QC_FIELD_PRESCRIBED) {
+        QC_CUDA(cudaMemcpyAsync(pl->psi.p, psi_in, pl->state_elems * sizeof(cd), cudaMemcpyHostToDevice, st));
+        int32_t rc = run_sweep(pl, args, false);
+        if (rc) return rc;
+        QC_CUDA(cudaMemcpyAsync(psi_out, pl->psi.p, pl->state_elems * sizeof(cd), cudaMemcpyDeviceToHost, st));
+        QC_CUDA(cudaStreamSynchronize(st));
+        return QC_OK;
+    }
+    // Runs are independent: cut the batch into chunks and pipeline H2D(i+1) / kernel(i) / D2H(i-1) over
+    // three streams so that the PCIe copies hide behind the propagation.
+    if (!ctx->aux_ready) {
+        for (auto &a : ctx->aux) QC_CUDA(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+        for (auto &e : ctx->aux_ev) QC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->aux_ready = true;
+    }
+    cudaStream_t streams[3] = {st, ctx->aux[0], ctx->aux[1]};
+    QC_CUDA(cudaEventRecord(ctx->aux_ev[0], st));
+    QC_CUDA(cudaStreamWaitEvent(ctx->aux[0], ctx->aux_ev[0], 0));
+    QC_CUDA(cudaStreamWaitEvent(ctx->aux[1], ctx->aux_ev[0], 0));
+    const size_t per_run = (size_t)d.nb * d.nlevs * d.np;
+    int k = 0;
+    for (int first = 0; first < d.batch; first += chunk, ++k) {
+        const int count = d.batch - first < chunk ? d.batch - first : chunk;
+        cudaStream_t s = streams[k % 3];
+        const size_t off = (size_t)first * per_run;
+        QC_CUDA(cudaMemcpyAsync(pl->psi.p + off, reinterpret_cast<const cd *>(psi_in) + off, count * per_run * sizeof(cd),
+                                cudaMemcpyHostToDevice, s));
+        ApplyOpts ap;
+        ap.run_first = first;
+        ap.run_count = count;
+        ap.stream = s;
+        int32_t rc = run_sweep(pl, args, false, ap);
+        if (rc) return rc;
+        QC_CUDA(cudaMemcpyAsync(reinterpret_cast<cd *>(psi_out) + off, pl->psi.p + off, count * per_run * sizeof(cd),
+                                cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < 2; ++i) {
+        QC_CUDA(cudaEventRecord(ctx->aux_ev[1 + i], ctx->aux[i]));
+        QC_CUDA(cudaStreamWaitEvent(st, ctx->aux_ev[1 + i], 0));
+    }
     QC_CUDA(cudaStreamSynchronize(st));
     return QC_OK;
 }

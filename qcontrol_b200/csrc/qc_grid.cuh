@@ -28,6 +28,7 @@ namespace qc {
 
 struct GridParams {
     int batch, nch, nt_max;
+    int run_first, run_count;    // this launch covers runs [run_first, run_first + run_count)
     int hf_hide, renorm, field_mode, reversed_E, write_E_base;
     int l_first, nsteps;
     int single_step;             // 1: qc_prop_step semantics (explicit E, no transform / renorm)
@@ -200,8 +201,8 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
     double *s_red = s_xp + C::MAXCH;              // 32 doubles of reduction scratch
     double *s_kc = s_red + 32;                    // [16][TPL] k-space multiplier in this thread layout (both levels)
 
-    const int run = blockIdx.x;
-    if (run >= p.batch) return;
+    const int run = p.run_first + blockIdx.x;
+    if ((int)blockIdx.x >= p.run_count || run >= p.batch) return;
     const int k1p = t / R3;       // k1' : which pass-1 output row this thread transforms in pass 2
     const int n3p = t % R3;       // n3' (also the lane's index c inside its group in pass 3)
     // named barrier ids: 1,2 level-local transposes; 3,4 "stash of level n is full"; 5,6 "... released"
