@@ -1,0 +1,139 @@
+"""GPU edge cases the reference's domain has: ragged batches (runs of different length in one plan),
+unusual polynomial orders, the smallest / single-run batches, and the error behaviour of the C ABI."""
+import copy
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import qc_oracle as qo
+from tests.golden.gen_golden import conf_krotov, conf_ut_jx
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from qcontrol_b200 import engine
+    c = engine.Context(0)
+    yield c
+    c.close()
+
+
+def _rows(hist):
+    return np.array([[r.it, r.goal_close, r.Fsm, r.E_int, r.J] for r in hist])
+
+
+def test_ragged_krotov_batch(ctx):
+    """Three Krotov runs of different length (nt = 40, 64, 25) and amplitude in ONE plan: each must equal
+    the oracle run on its own (per-run nt, per-run interpolation table, padded trajectories)."""
+    from qcontrol_b200 import control
+    pbs = []
+    for nt, scale in ((40, 1.0), (64, 0.7), (25, 1.3)):
+        user = conf_krotov(nt, 2, np_=256)
+        user["fitter"]["propagation"]["E0"] *= scale
+        pbs.append(qo.make_problem(user))
+    gb = control.GridBatch(pbs, ctx=ctx)
+    hist = gb.run_krotov()
+    for b, pb in enumerate(pbs):
+        ref = qo.Fitter(pb).run()
+        got, want = _rows(hist[b]), _rows(ref)
+        assert got.shape == want.shape
+        assert np.allclose(got, want, rtol=1e-9, atol=0), (b, got - want)
+        for r, q in zip(hist[b], ref):
+            assert np.allclose(r.E_tlist, q.E_tlist, rtol=1e-9, atol=1e-9 * np.abs(q.E_tlist).max())
+    gb.close()
+
+
+def test_ragged_unit_transform_batch(ctx):
+    """The T-sweep shape of input_batch/inp_Jx_*: runs with different T (hence nt, sigma, nu) in one plan."""
+    from qcontrol_b200 import control
+    pbs = []
+    for k, T in enumerate((2.5e-13, 4.1e-13, 3.3e-13)):
+        user = conf_ut_jx(1, 2, T=T, w_list=tuple(np.random.default_rng(1000 + k).uniform(-2, 2, 3)))
+        user["nt_auto"] = True
+        user["fitter"]["h_lambda"] = 5e-4
+        pbs.append(qo.make_problem(user, apply_auto=True))
+    assert len({p.nt for p in pbs}) == 3
+    nb = control.NLevelBatch(pbs, ctx=ctx)
+    hist = nb.run_unit_transform()
+    for b, pb in enumerate(pbs):
+        want = _rows(qo.Fitter(pb).run())
+        got = _rows(hist[b])
+        assert got.shape == want.shape and np.allclose(got[1:], want[1:], rtol=1e-8, atol=0), (b, got - want)
+    nb.close()
+
+
+@pytest.mark.parametrize("nch", [2, 8, 32, 128])
+def test_polynomial_orders(ctx, nch):
+    """nch from the smallest legal value to the largest the plan accepts (np = 512, one step)."""
+    from qcontrol_b200 import engine, math_base
+    np_ = 512
+    rng = np.random.default_rng(nch)
+    dx = 5.0 / (np_ - 1)
+    x = (np.arange(np_) - (np_ - 1) / 2) * dx
+    akx2 = qo.initak(np_, dx, 2, 1) * (-qo.HART_TO_CM / (2.0 * 0.5 * qo.DALT_TO_AU))
+    v = np.stack([2e4 * (1 - np.exp(-x)) ** 2, 1e4 * (1 - np.exp(-(x + 0.17))) ** 2 + 2e4])
+    psi = (rng.standard_normal((2, np_)) + 1j * rng.standard_normal((2, np_))) * np.exp(-x ** 2 / 0.2)
+    psi /= np.sqrt(dx * np.sum(np.abs(psi) ** 2))
+    emax, emin = float(v.max() + abs(akx2[np_ // 2 - 1]) + 50.0), -50.0
+    t_sc = 0.05 * nch
+    pl = engine.Plan(ctx, engine.HAMIL_NONTRIV, np_, 2, 1, nch, 1, 1)
+    pl.set_static(v, np.ascontiguousarray(akx2.real), None, dx)
+    xp, dv = math_base.newton_table(nch, t_sc)
+    pl.set_poly(0, xp, dv, emin, emax, t_sc, 4886.0)
+    pl.set_state(psi[None, None])
+    pl.prop_step(0, -17.5)
+    out = pl.get_state()[0, 0]
+    pb = qo.Problem(hamil="ntriv", ntriv=1, np_=np_, nlevs=2, nb=1, dx=dx, v=v, vmin=np.zeros(2), akx2=akx2, nch=nch)
+    ref = qo.newton_propagate(pb, psi, t_sc, emin, emax, np.float64(-17.5), 4886.0, np.float64(-17.5))
+    assert np.sqrt(dx * np.sum(np.abs(out - ref) ** 2)) <= 1e-10
+    pl.close()
+
+
+def test_zero_state_is_not_renormalised(ctx):
+    """A zero wavefunction stays zero: the renormalisation is skipped when the norm is 0 (propagation.py:430)."""
+    from qcontrol_b200 import control
+    pb = qo.make_problem(conf_krotov(8, 0, np_=256))
+    pb.psi0 = np.zeros_like(pb.psi0)
+    pb.task_type = "trans_wo_control"
+    gb = control.GridBatch([pb], ctx=ctx, store_traj=False)
+    out = gb.propagate(control.FORWARD)
+    assert np.all(out == 0) and np.all(np.isfinite(out.view(np.float64)))
+    gb.close()
+
+
+def test_abi_error_behaviour(ctx):
+    """Errors are return codes with a message (-> QcError), never a silent fallback or a crash."""
+    from qcontrol_b200 import engine
+    from qcontrol_b200._lib import QcError
+    for kw, frag in ((dict(np_=300), "np in"), (dict(np_=4096), "np in"), (dict(nch=48), "power of two"), (dict(nb=2), "nlevs=2, nb=1"),
+                     (dict(batch=0), "batch=0")):
+        args = dict(hamil=engine.HAMIL_NONTRIV, np_=512, nlevs=2, nb=1, nch=64, batch=2, nt_max=4)
+        args.update(kw)
+        with pytest.raises(QcError) as e:
+            engine.Plan(ctx, **args)
+        assert e.value.code == -1 and frag in str(e.value)
+    with pytest.raises(QcError) as e:
+        engine.Plan(ctx, engine.HAMIL_BH_X, 8, 2, 2, 8, 1, 4)
+    assert "np=1" in str(e.value)
+    with pytest.raises(QcError) as e:
+        engine.Plan(ctx, engine.HAMIL_BH_X, 1, 2, 2, 8, 1, 4, hf_hide=True)
+    assert "hf_hide" in str(e.value)
+    pl = engine.Plan(ctx, engine.HAMIL_NONTRIV, 512, 2, 1, 64, 2, 4)
+    with pytest.raises(QcError) as e:
+        pl.sweep(0, 0, 1, 1)
+    assert e.value.code == -3 and "qc_set_static" in str(e.value)
+    pl.set_static(np.zeros((2, 512)), np.zeros(512), None, 0.01)
+    with pytest.raises(QcError) as e:
+        pl.sweep(0, 0, 1, 1)
+    assert e.value.code == -3 and "polynomial slot" in str(e.value)
+    with pytest.raises(QcError) as e:
+        pl.set_poly(0, np.zeros(64), np.zeros(64, complex), 5.0, 1.0, 0.1)
+    assert "emax" in str(e.value)
+    with pytest.raises(QcError):
+        pl.sweep(0, engine.FIELD_KROTOV_FWD, 1, 1, True, 1, 0)      # no trajectory buffers in this plan
+    with pytest.raises(QcError):
+        pl.set_control(0.0, 4)                                        # h_lambda = 0
+    with pytest.raises(QcError):
+        pl.set_control(1.0, 99)                                       # nt > nt_max
+    pl.close()
