@@ -124,8 +124,7 @@ __device__ __forceinline__ void dft16(cd *a) {
 }
 
 
-// ---- 16-point DFT split into its two radix-4 stages, so that twiddling and the shared-memory
-// ---- traffic around it can be streamed group by group (keeps register live ranges short)
+// constant twiddles w16^(ka*nb) between the two radix-4 stages of the 16-point DFT (element a[4*ka + nb])
 template <bool INV>
 __device__ __forceinline__ void dft16_internal_twiddles(cd *a) {
     const cd w1 = cmk(QC_COS_PI_8, -QC_SIN_PI_8);   // w16^1
@@ -142,97 +141,10 @@ __device__ __forceinline__ void dft16_internal_twiddles(cd *a) {
     a[15] = twmul<INV>(a[15], w9);
 }
 
-// acc + y * w (forward) or acc + y * conj(w) (inverse), as four FMAs
-template <bool INV>
-__device__ __forceinline__ cd cfma_tw(cd y, cd w, cd acc) {
-    return INV ? cmk(fma(y.x, w.x, fma(y.y, w.y, acc.x)), fma(y.y, w.x, fma(-y.x, w.y, acc.y)))
-               : cmk(fma(y.x, w.x, fma(-y.y, w.y, acc.x)), fma(y.x, w.y, fma(y.y, w.x, acc.y)));
-}
-// 2a - b
-__device__ __forceinline__ cd ctwice_minus(cd a, cd b) { return cmk(fma(2.0, a.x, -b.x), fma(2.0, a.y, -b.y)); }
-
-struct TwBase {       // w^0..w^3 and q = w^4 of one root
-    cd b1, b2, b3, q;
-};
-__device__ __forceinline__ TwBase tw_base(cd w_in) {
-    double wx = w_in.x, wy = w_in.y;
-    asm volatile("" : "+d"(wx), "+d"(wy));      // the root is loop invariant: keep its powers from being hoisted
-    TwBase t;
-    t.b1 = cmk(wx, wy);
-    t.b2 = cmul(t.b1, t.b1);
-    t.b3 = cmul(t.b2, t.b1);
-    t.q = cmul(t.b2, t.b2);
-    return t;
-}
-
-// a (natural order) -> DFT16 -> element k multiplied by w^k -> sink(k, value), k in groups {ka, ka+4, ka+8, ka+12}
-template <bool INV, class Sink>
-__device__ __forceinline__ void dft16_twiddle_out(cd *a, const cd w, Sink sink) {
-#pragma unroll
-    for (int nb = 0; nb < 4; ++nb) dft4<INV>(a[nb], a[4 + nb], a[8 + nb], a[12 + nb]);
-    dft16_internal_twiddles<INV>(a);
-    const TwBase tb = tw_base(w);
-#pragma unroll
-    for (int ka = 0; ka < 4; ++ka) {
-        dft4<INV>(a[4 * ka], a[4 * ka + 1], a[4 * ka + 2], a[4 * ka + 3]);   // X[ka + 4 kb] in a[4 ka + kb]
-        cd r = ka == 0 ? tb.q : (ka == 1 ? tb.b1 : (ka == 2 ? tb.b2 : tb.b3));
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
-            if (ka == 0 && kb == 0) {
-                sink(0, a[0]);
-            } else {
-                sink(ka + 4 * kb, cmul(a[4 * ka + kb], r));
-                if (kb < 3) r = cmul(r, tb.q);
-            }
-        }
-    }
-}
-
-// source(k) * conj(w^k) -> inverse DFT16 -> a (natural order); loads come in groups {nb, nb+4, nb+8, nb+12}
-template <class Source>
-__device__ __forceinline__ void dft16_twiddle_in_inv(cd *a, const cd w, Source source) {
-    const TwBase tb = tw_base(w);
-#pragma unroll
-    for (int nb = 0; nb < 4; ++nb) {
-        cd r = nb == 0 ? tb.q : (nb == 1 ? tb.b1 : (nb == 2 ? tb.b2 : tb.b3));
-        cd x0 = source(nb), x1 = source(nb + 4), x2 = source(nb + 8), x3 = source(nb + 12);
-        if (nb == 0) {
-            x1 = cmulc(x1, r);
-            r = cmul(r, tb.q);
-            x2 = cmulc(x2, r);
-            r = cmul(r, tb.q);
-            x3 = cmulc(x3, r);
-        } else {
-            x0 = cmulc(x0, r);
-            r = cmul(r, tb.q);
-            x1 = cmulc(x1, r);
-            r = cmul(r, tb.q);
-            x2 = cmulc(x2, r);
-            r = cmul(r, tb.q);
-            x3 = cmulc(x3, r);
-        }
-        dft4<true>(x0, x1, x2, x3);
-        a[nb] = x0;
-        a[4 + nb] = x1;
-        a[8 + nb] = x2;
-        a[12 + nb] = x3;
-    }
-    dft16_internal_twiddles<true>(a);
-#pragma unroll
-    for (int ka = 0; ka < 4; ++ka) dft4<true>(a[4 * ka], a[4 * ka + 1], a[4 * ka + 2], a[4 * ka + 3]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = i + 1; j < 4; ++j) {
-            cd t = a[4 * i + j];
-            a[4 * i + j] = a[4 * j + i];
-            a[4 * j + i] = t;
-        }
-}
-
-// ---- the same two streamed transforms with the twiddles w^k taken from a per-thread table instead of a
-// ---- running product.  TwSrc::prefetch(g) starts fetching the four twiddles {w^g, w^(g+4), w^(g+8), w^(g+12)}
-// ---- of radix-4 group g, TwSrc::get(w4) waits for them (tensor-memory table, see qc_grid.cuh).
+// ---- 16-point DFTs streamed with the shared-memory traffic around them, twiddles w^k from a per-thread table.
+// ---- TwSrc::prefetch(g) starts fetching the four twiddles {w^g, w^(g+4), w^(g+8), w^(g+12)} of radix-4 group g,
+// ---- TwSrc::get(w4) waits for them (tensor-memory table, see qc_grid.cuh).  Working group by group keeps
+// ---- register live ranges short: each group's outputs leave for shared memory as soon as they exist.
 template <bool INV, class TwSrc, class Sink>
 __device__ __forceinline__ void dft16_table_out(cd *a, TwSrc &tw, Sink sink) {
 #pragma unroll
@@ -256,7 +168,8 @@ __device__ __forceinline__ void dft16_table_out(cd *a, TwSrc &tw, Sink sink) {
 
 // inverse 4-point DFT of y_i * conj(w_i) with the twiddles of inputs 2 and 3 fused into the first butterfly
 // stage: t0 = x0 + y2 conj(w2) (four FMAs), t1 = 2 x0 - t0 (two FMAs) instead of a complex multiply and two
-// complex additions -- four instructions fewer per group and the FP64 pipe issues FMAs instead of adds.
+// complex additions -- four instructions fewer per group.  (The same fusion inside the constant-twiddle
+// stage of dft16 was measured slower: it lengthens the dependency chains of a latency-bound kernel.)
 template <bool FIRST_IS_ONE>
 __device__ __forceinline__ void dft4_inv_conj_twiddled(cd &y0, cd &y1, cd &y2, cd &y3, const cd *w) {
     const cd x0 = FIRST_IS_ONE ? y0 : cmulc(y0, w[0]);

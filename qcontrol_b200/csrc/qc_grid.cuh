@@ -1,27 +1,32 @@
 // Kernel A: fused Newton-polynomial time stepper for the two-level FFT-grid
 // Hamiltonian (Hamil2DNonTrivial, hamil_2d.py:34-73).
 //
-// One CTA owns one run (one two-level wavefunction) for a whole launch of
-// `nsteps` time steps.  2*TPL threads, TPL = N/16: thread (level, t) keeps the 16
-// grid points x = t + TPL*n1 of its level in registers, for both the recurrence
-// vector phi and the accumulator psi.  Per polynomial order the only data that
-// leaves the register file are the four FFT transposes and the phi stash, all in
-// shared memory; HBM is touched once per time step (trajectory slice in/out).
+// One CTA owns one run (one two-level wavefunction) for a whole launch of `nsteps` time steps.
+// 2*TPL threads, TPL = N/16: thread (level, t) owns the 16 grid points x = t + TPL*n1 of its level.
 //
-// FFT: N = 16*16*R3 (R3 = N/256), decimation in frequency forward, the exact
-// mirror inverse, so no reordering pass is needed and the k-space multiply runs
-// on the permuted layout with a per-thread register copy of the multiplier.
-// Twiddles are NOT read from a table: shared-memory bandwidth is the binding
-// resource of this kernel (ncu, profiles/r01a_*), the FP64 pipe has slack, so
-// each thread keeps the two roots it needs (w_N^t and w_{16 R3}^{n3}) in
-// registers and generates their powers with a running complex product.
+// Where the data lives
+//   registers      the recurrence vector phi (16 complex), the diagonal d(x) and the k-space multiplier
+//   tensor memory  per thread 256 columns: the accumulator psi, the thread's own copy of phi, and the two
+//                  twiddle tables w_N^(k t), w_{16 R3}^(k n3) (tcgen05.st once, tcgen05.ld per use).  TMEM
+//                  has its own datapath (measured 790 B/clk/SM read, 930 B/clk/SM write on B200,
+//                  tools/tmem_bw.cu), so none of this competes with shared memory
+//   shared memory  only what has to cross threads: the four FFT transposes per polynomial order and the
+//                  phi hand-over between the two levels (coupling term -E*phi_other)
+//   HBM            once per time step: trajectory slice in / out (Krotov), the state at launch begin / end
 //
-// Synchronisation (N >= 512): the two levels are separate groups of warps that
-// only meet at the coupling term -E*phi_other.  Each level synchronises its own
-// transposes on a private named barrier; the phi stash is handed over with a
-// full/released pair of named barriers (bar.arrive / bar.sync), so neither level
-// ever waits for the other unless it is a whole polynomial order ahead.
+// FFT: N = 16*16*R3 (R3 = N/256), decimation in frequency forward, the exact mirror inverse, so no
+// reordering pass is needed and the k-space multiply runs on the permuted layout.
+//
+// Synchronisation (N >= 512): the two levels are separate groups of warps that only meet at the coupling
+// term.  Each level synchronises its own transposes on a private named barrier; phi is handed over with a
+// full / released pair of named barriers (bar.arrive / bar.sync), so neither level waits for the other
+// unless it is a whole polynomial order ahead.
+//
+// History of this kernel with ncu evidence: profiles/r01a (twiddle tables in shared memory, 0.41 of the
+// FP64 peak), r01c (register power chains, 0.48), r01d/r01e (TMEM accumulator and tables, 0.52).
 #pragma once
+#include <cstdint>
+
 #include "qc_fft.cuh"
 
 namespace qc {
@@ -69,9 +74,11 @@ struct GridCfg {
     static constexpr int NTHREADS = 2 * TPL;
     static constexpr int MAXCH = 128;
     static constexpr bool NAMED = TPL >= 32;    // a level is made of whole warps: per-level named barriers
-    // shared memory (complex elements): per level A, B, S ; then dv, xp, reduction scratch, k-space multiplier
+    static constexpr int TM_COLS = NTHREADS > 128 ? 512 : 256;   // 256 TMEM columns per warp slot
+    // shared memory (complex elements): per level transpose buffers A, B and the phi hand-over S ;
+    // then dv, xp and 32 doubles of reduction scratch (the last one carries the TMEM base address)
     static constexpr size_t SMEM_BYTES =
-        sizeof(cd) * (size_t)(2 * (2 * BUF + N)) + sizeof(double) * (size_t)(3 * MAXCH + 32 + N);
+        sizeof(cd) * (size_t)(2 * (2 * BUF + N)) + sizeof(double) * (size_t)(3 * MAXCH + 32);
 };
 
 // skewed position of element (k2, n3) inside a lane group's private 16*R3 region
@@ -87,12 +94,8 @@ __device__ __forceinline__ void bar_arrive(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-#ifdef QC_TMEM
-// ---- Tensor memory as a per-thread scratchpad ------------------------------------------------------
-// The accumulator psi and the thread's own copy of phi live in TMEM between their uses: TMEM has its own
-// datapath (tcgen05.ld / tcgen05.st), so this traffic does not compete with the shared-memory pipe that
-// bounds the kernel, and it frees 64 registers (no spills, k-space multiplier back in registers).
-// Each thread owns one TMEM lane (warp w -> lanes 32*(w%4)..+31) and 128 columns: 64 for psi, 64 for phi.
+// ---- tensor memory as a per-thread scratchpad -----------------------------------------------------------
+// Each thread owns one TMEM lane (warp w -> lanes 32*(w%4)..+31; warps w and w+4 use different columns).
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -137,7 +140,7 @@ struct TmemTwiddles {
         tmem_unpack_c4(r, w4);
     }
 };
-// fill the table of one root: powers by repeated squaring / pairing (depth log2 k), stored group-major
+// fill the table of one root: powers by pairing (depth log2 k, ~4 roundings), stored group-major
 __device__ __forceinline__ void tmem_fill_twiddles(uint32_t taddr, const cd w) {
     cd pw[16];
     pw[0] = cmk(1.0, 0.0);
@@ -148,19 +151,6 @@ __device__ __forceinline__ void tmem_fill_twiddles(uint32_t taddr, const cd w) {
     for (int g = 0; g < 4; ++g) {
         cd grp[4] = {pw[g], pw[g + 4], pw[g + 8], pw[g + 12]};
         tmem_store_c4(taddr + 16 * g, grp);
-    }
-}
-#endif
-
-// a[k] *= w^k (k = 1..15) with a running product; conjugated for the inverse transform
-template <bool INV>
-__device__ __forceinline__ void twiddle_powers(cd *a, const cd w) {
-    cd pw = w;
-    a[1] = twmul<INV>(a[1], pw);
-#pragma unroll
-    for (int k = 2; k < 16; ++k) {
-        pw = cmul(pw, w);
-        a[k] = twmul<INV>(a[k], pw);
     }
 }
 
@@ -199,13 +189,12 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
     cd *s_dv = sm + 2 * (2 * BUF + N);
     double *s_xp = reinterpret_cast<double *>(s_dv + C::MAXCH);
     double *s_red = s_xp + C::MAXCH;              // 32 doubles of reduction scratch
-    double *s_kc = s_red + 32;                    // [16][TPL] k-space multiplier in this thread layout (both levels)
 
     const int run = p.run_first + blockIdx.x;
     if ((int)blockIdx.x >= p.run_count || run >= p.batch) return;
     const int k1p = t / R3;       // k1' : which pass-1 output row this thread transforms in pass 2
     const int n3p = t % R3;       // n3' (also the lane's index c inside its group in pass 3)
-    // named barrier ids: 1,2 level-local transposes; 3,4 "stash of level n is full"; 5,6 "... released"
+    // named barrier ids: 1,2 level-local transposes; 3,4 "phi of level n is available"; 5,6 "... released"
     const int BAR_LEVEL = 1 + lev, BAR_FULL_OWN = 3 + lev, BAR_FULL_OTH = 4 - lev, BAR_REL_OWN = 5 + lev,
               BAR_REL_OTH = 6 - lev;
 
@@ -224,15 +213,10 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
     double ph_s, ph_c;
     sincos(-2.0 * t_sc * (emax + emin) / (emax - emin), &ph_s, &ph_c);   // phys_base.py:174
     const cd phase = cmk(ph_c, ph_s);
-    const cd w1 = p.tw1[S1 + t];            // w_N^t          (forward value)
-    const cd w2 = p.tw2[R3 + n3p];          // w_{16 R3}^{n3'}
 
-    // per-thread constants: diagonal d(x) = c1*(v(x) +- eL) - c2 (registers) and the k-space multiplier
-    // (shared memory: the register file cannot hold it beside phi, psi and d without spilling)
-    double dcoef[16];
-#ifdef QC_KC_REGS
-    double kc[16];
-#endif
+    // per-thread constants in registers: diagonal d(x) = c1*(v(x) +- eL) - c2 and the k-space multiplier
+    // c1/N * akx2[k] at the (permuted) frequencies this thread holds after the forward transform
+    double dcoef[16], kc[16];
     {
         const double *vr = p.v + p.v_stride * run + (long long)lev * N;
         const double sgn = lev == 0 ? eL : -eL;                  // hamil_2d.py:50-51, 66-67
@@ -243,11 +227,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
         for (int e = 0; e < 16; ++e) {
             const int q = e / R3, k3 = e % R3;
             const int k = k1p + 16 * (n3p * Q + q) + 256 * k3;
-#ifdef QC_KC_REGS
             kc[e] = p.kin[k] * kscale;
-#else
-            if (lev == 0) s_kc[e * TPL + t] = p.kin[k] * kscale;
-#endif
         }
     }
 
@@ -257,14 +237,12 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) psi[n1] = src[t + TPL * n1];
     }
-#ifdef QC_TMEM
-    // one warp allocates 128 columns per warp slot (warps w and w+4 share a lane quadrant)
-    constexpr int TM_COLS = C::NTHREADS > 128 ? 512 : 256;     // 256 columns per warp slot: psi, phi, two twiddle tables
+    // ---- tensor memory: one warp allocates, everybody learns the base address ------------------------
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_red + 30);
     if (tid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          (uint32_t)__cvta_generic_to_shared(s_tmem)),
-                     "n"(TM_COLS)
+                     "n"(C::TM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -276,10 +254,9 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
     const uint32_t t_psi = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 256);
     const uint32_t t_phi = t_psi + 64;
     const uint32_t t_tw1 = t_psi + 128, t_tw2 = t_psi + 192;
-    tmem_fill_twiddles(t_tw1, w1);
-    tmem_fill_twiddles(t_tw2, w2);
+    tmem_fill_twiddles(t_tw1, p.tw1[S1 + t]);        // w_N^t          (host-computed root, forward value)
+    tmem_fill_twiddles(t_tw2, p.tw2[R3 + n3p]);      // w_{16 R3}^{n3'}
     tmem_wait_st();
-#endif
     __syncthreads();
 
     const cd *traj_in = p.traj_in ? p.traj_in + (long long)run * (p.nt_max + 1) * N : nullptr;
@@ -342,68 +319,52 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
         const double cE = c1 * E;
         const double cEi = c1 * Ei;
 
-        // ---- Newton recurrence (phys_base.py:158-172) ------------------------
+        // ---- Newton recurrence (phys_base.py:158-172): phi = psi, psi <- dv0 * psi (parked in TMEM) -----
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             a[i] = psi[i];
             psi[i] = cmul(psi[i], s_dv[0]);
         }
-#ifdef QC_TMEM
 #pragma unroll
         for (int c4 = 0; c4 < 16; c4 += 4) tmem_store_c4(t_psi + c4 * 4, psi + c4);
-#endif
         for (int j = 0; j <= last_j; ++j) {
             const double xpj = s_xp[j];
             const cd dvj = s_dv[j + 1];
-            // keep the swizzled transpose addresses from being hoisted out of the loop (64 registers):
-            // they are two integer instructions each on an otherwise idle pipe
-            // stash phi (own slots, natural x order) once the other level has read the previous one
+            // hand phi over to the other level (shared memory) once it has read the previous one, and keep
+            // an own copy in TMEM for the pointwise phase
             if (NAMED && j > 0) bar_sync(BAR_REL_OWN, C::NTHREADS);
 #pragma unroll
             for (int n1 = 0; n1 < 16; ++n1) stash[t + TPL * n1] = a[n1];
-#ifdef QC_TMEM
 #pragma unroll
-            for (int c4 = 0; c4 < 16; c4 += 4) tmem_store_c4(t_phi + c4 * 4, a + c4);   // own copy, read back below
-#endif
-            if (NAMED) bar_arrive(BAR_FULL_OWN, C::NTHREADS);   // producer side of a named barrier: no fence (FA3 pattern)
-            // pass 1 : DFT over n1, twiddle w_N^(k1*t)
-#ifdef QC_TMEM
+            for (int c4 = 0; c4 < 16; c4 += 4) tmem_store_c4(t_phi + c4 * 4, a + c4);
+            if (NAMED) bar_arrive(BAR_FULL_OWN, C::NTHREADS);   // producer side of a named barrier (no fence needed)
+            // pass 1 : DFT over n1, twiddle w_N^(k1*t), transpose
             {
                 TmemTwiddles tw(t_tw1);
                 dft16_table_out<false>(a, tw, [&](int k1, cd val) { bufA[k1 * S1 + t] = val; });
             }
-#else
-            dft16_twiddle_out<false>(a, w1, [&](int k1, cd val) { bufA[k1 * S1 + t] = val; });
-#endif
             if (NAMED) bar_sync(BAR_LEVEL, TPL); else __syncthreads();              // (#1)
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) a[n2] = bufA[k1p * S1 + n2 * R3 + n3p];
-            // pass 2 : DFT over n2, twiddle w_{16 R3}^(k2*n3)
+            // pass 2 : DFT over n2, twiddle w_{16 R3}^(k2*n3), transpose inside the R3-lane group
             if (R3 == 1) dft16<false>(a);
             if (R3 > 1) {
                 __syncwarp();
-#ifdef QC_TMEM
                 {
                     TmemTwiddles tw(t_tw2);
                     dft16_table_out<false>(a, tw, [&](int k2, cd val) { bufA[k1p * S1 + pos2<R3, Q>(k2, n3p)] = val; });
                 }
-#else
-                dft16_twiddle_out<false>(a, w2, [&](int k2, cd val) { bufA[k1p * S1 + pos2<R3, Q>(k2, n3p)] = val; });
-#endif
                 __syncwarp();
 #pragma unroll
                 for (int e = 0; e < 16; ++e)
                     a[e] = bufA[k1p * S1 + pos2<R3, Q>(n3p * Q + e / R3, e % R3)];
-                // pass 3 : Q DFTs of size R3 over n3 ; k-space multiply ; inverse pass 3
+                // pass 3 : Q DFTs of size R3 over n3
 #pragma unroll
                 for (int q = 0; q < Q; ++q) dft<R3, false>(a + q * R3);
             }
+            // k-space: kinetic multiplier (with c1 and the 1/N of the inverse transform folded in)
 #pragma unroll
-#ifdef QC_KC_REGS
             for (int e = 0; e < 16; ++e) a[e] = cscale(a[e], kc[e]);
-#else
-            for (int e = 0; e < 16; ++e) a[e] = cscale(a[e], s_kc[e * TPL + t]);
-#endif
             if (R3 > 1) {
 #pragma unroll
                 for (int q = 0; q < Q; ++q) dft<R3, true>(a + q * R3);
@@ -411,35 +372,24 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
                 for (int e = 0; e < 16; ++e)
                     bufB[k1p * S1 + pos2<R3, Q>(n3p * Q + e / R3, e % R3)] = a[e];
                 __syncwarp();
-#ifdef QC_TMEM
                 {
-                    TmemTwiddles tw(t_tw2);
+                    TmemTwiddles tw(t_tw2);       // inverse pass 2 with its conjugate twiddles on the load side
                     dft16_table_in_inv(a, tw, [&](int k2) { return bufB[k1p * S1 + pos2<R3, Q>(k2, n3p)]; });
                 }
-#else
-                dft16_twiddle_in_inv(a, w2, [&](int k2) { return bufB[k1p * S1 + pos2<R3, Q>(k2, n3p)]; });
-#endif
                 __syncwarp();
             }
-            // inverse pass 2
             if (R3 == 1) dft16<true>(a);
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) bufB[k1p * S1 + n2 * R3 + n3p] = a[n2];
             if (NAMED) bar_sync(BAR_LEVEL, TPL); else __syncthreads();              // (#2)
             // inverse pass 1 -> kinetic term (already scaled by c1) at x = t + TPL*n1
-#ifdef QC_TMEM
             {
                 TmemTwiddles tw(t_tw1);
                 dft16_table_in_inv(a, tw, [&](int k1) { return bufB[k1 * S1 + t]; });
             }
-#else
-            dft16_twiddle_in_inv(a, w1, [&](int k1) { return bufB[k1 * S1 + t]; });
-#endif
-            // pointwise part (hamil_2d.py:60-71, phys_base.py:98-111) and accumulation (phys_base.py:170-172)
+            // pointwise part (hamil_2d.py:60-71, phys_base.py:98-111) and accumulation (phys_base.py:170-172),
+            // in chunks of four grid points: psi and own phi from TMEM, the other level's phi from shared memory
             if (NAMED) bar_sync(BAR_FULL_OTH, C::NTHREADS);
-            // in chunks of four grid points: the compiler otherwise hoists all 32 shared loads above the
-            // arithmetic and spills (the register file holds phi, psi and d with little to spare)
-#ifdef QC_TMEM
             tmem_wait_st();
 #pragma unroll
             for (int c4 = 0; c4 < 16; c4 += 4) {
@@ -459,7 +409,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
                     cd r;
                     r.x = fma(dd, own4[i].x, fma(-cE, oth4[i].x, a[n1].x));
                     r.y = fma(dd, own4[i].y, fma(-cE, oth4[i].y, a[n1].y));
-                    if (p.cplx_coupling) {
+                    if (p.cplx_coupling) {           // orig=True form of hamil_2d.py:40-47 (uniform branch, off in sweeps)
                         r.x = fma(cEi, oth4[i].y, r.x);
                         r.y = fma(-cEi, oth4[i].x, r.y);
                     }
@@ -468,34 +418,12 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
                 }
                 tmem_store_c4(t_psi + c4 * 4, acc4);
             }
-#else
-#pragma unroll
-            for (int c4 = 0; c4 < 16; c4 += 4) {
-#pragma unroll
-                for (int n1 = c4; n1 < c4 + 4; ++n1) {
-                    const cd own = stash[t + TPL * n1];
-                    const cd oth = stash_other[t + TPL * n1];
-                    const double dd = dcoef[n1] - xpj;
-                    cd r;
-                    r.x = fma(dd, own.x, fma(-cE, oth.x, a[n1].x));
-                    r.y = fma(dd, own.y, fma(-cE, oth.y, a[n1].y));
-                    if (p.cplx_coupling) {           // orig=True form of hamil_2d.py:40-47 (uniform branch, off in sweeps)
-                        r.x = fma(cEi, oth.y, r.x);
-                        r.y = fma(-cEi, oth.x, r.y);
-                    }
-                    a[n1] = r;
-                    psi[n1] = cfma(dvj, r, psi[n1]);
-                }
-                asm volatile("" ::: "memory");
-            }
-#endif
             if (NAMED) {
                 if (j < last_j) bar_arrive(BAR_REL_OTH, C::NTHREADS);
             } else {
-                __syncthreads();                                                   // (#3) stash reuse
+                __syncthreads();                                                   // (#3) hand-over buffer reuse
             }
         }
-#ifdef QC_TMEM
         tmem_wait_st();
 #pragma unroll
         for (int c4 = 0; c4 < 16; c4 += 4) {
@@ -504,7 +432,6 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
             tmem_wait_ld();
             tmem_unpack_c4(rp, psi + c4);
         }
-#endif
         // ---- final phase (phys_base.py:174-176), norms, renormalisation --------
         double nrm = 0.0;
 #pragma unroll
@@ -555,13 +482,11 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) dst[t + TPL * n1] = psi[n1];
     }
-#ifdef QC_TMEM
     tmem_wait_st();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (tid < 32)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TM_COLS) : "memory");
-#endif
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TM_COLS) : "memory");
 }
 
 }  // namespace qc
