@@ -173,6 +173,9 @@ int32_t qc_instrument(qc_plan *plan, const double *E_full, double two_m, int32_t
 
 /* Field used at each step of the last sweep(s): E_out[batch][nt_max+1] complex (E_tlist, fitter.py:281,326). */
 int32_t qc_get_fields(qc_plan *plan, double *E_out);
+/* sum_{l=1..nt} |E_l|^2 of the fields of the last sweep, per run: out[batch] (E_int / dt, fitter.py:338-341),
+ * so that a batch can iterate without copying whole field lists to the host. */
+int32_t qc_field_integral(qc_plan *plan, double *out);
 /* Per-level norms before renormalisation, norms[batch][nb][nlevs] of the LAST step run (cnorm, propagation.py:424-429). */
 int32_t qc_get_norms(qc_plan *plan, double *norms);
 

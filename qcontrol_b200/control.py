@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import cmath
 import math
+import time
 from dataclasses import dataclass, field
 from typing import List, Sequence
 
@@ -447,10 +448,22 @@ class NLevelBatch(_BatchBase):
         h0 = p.h_lambda * RED_PLANCK_H / CM_TO_ERG if p.ntriv == -1 else p.h_lambda
         return IterRow(-1, float(abs(sc)), float(F0.real), float(Ei), float(F0.real - h0 * h0 * Ei), np.array(El))
 
-    def run_unit_transform(self, iter_max=None):
-        """optimal_control_unit_transform for every run (fitter.py:441-569, 709-778, 799-807)."""
+    def run_unit_transform(self, iter_max=None, keep_fields=True):
+        """optimal_control_unit_transform for every run (fitter.py:441-569, 709-778, 799-807).
+
+        keep_fields=True copies every run's field list to the host after every forward sweep (what
+        print_iter_point_fitter receives, and what the parity tests compare).  keep_fields=False is the
+        throughput mode for big batches whose reports only need the iteration table (plotting_flag
+        "tables_iter", input_batch/input_report.json:7): E_int is reduced on the device and the per-iteration
+        host work is a handful of numpy array operations, so the loop is bound by the sweeps themselves."""
         pl = self.plan
         B = self.B
+        kind = self.pbs[0].F_type
+        assert keep_fields or all(p.F_type == kind for p in self.pbs)
+        h0_all = np.array([p.h_lambda * RED_PLANCK_H / CM_TO_ERG if p.ntriv == -1 else p.h_lambda for p in self.pbs])
+        mode_dyn = np.array([p.h_lambda_mode == "dynamical" for p in self.pbs])
+        nb_runs = np.array([float(p.nb) for p in self.pbs])
+        t_steps = np.array([float(p.t_step) for p in self.pbs])
         hist: List[List[IterRow]] = [[self._initial_row(b)] for b in range(B)]
         self.errors = [""] * B
         done = np.zeros(B, bool)
@@ -471,6 +484,8 @@ class NLevelBatch(_BatchBase):
             base_rows.append(br)
         pl.set_s_env(self._pad(s_rows))
         it = 0
+        self.ctx.synchronize()
+        t_loop = time.perf_counter()
         while True:
             # ---- backward sweep from the goal basis (fitter.py:241-249) ----------------------------
             pl.snapshot_load(1)
@@ -484,31 +499,58 @@ class NLevelBatch(_BatchBase):
                             reversed_E=True)
             chi_init = pl.get_state()
             # ---- l == 0 of the forward sweep: h_lambda and a0 (fitter.py:712-737) -------------------
-            for b, p in enumerate(self.pbs):
-                h0 = p.h_lambda * RED_PLANCK_H / CM_TO_ERG if p.ntriv == -1 else p.h_lambda
-                if p.h_lambda_mode == "dynamical" and goal_close_abs[b]:
-                    h_lambda[b] = h0 * p.nb / math.sqrt(goal_close_abs[b])
+            if keep_fields:
+                for b, p in enumerate(self.pbs):
+                    h0 = p.h_lambda * RED_PLANCK_H / CM_TO_ERG if p.ntriv == -1 else p.h_lambda
+                    if p.h_lambda_mode == "dynamical" and goal_close_abs[b]:
+                        h_lambda[b] = h0 * p.nb / math.sqrt(goal_close_abs[b])
+                    else:
+                        h_lambda[b] = h0
+                    a0[b] = _a_value(p.F_type, p.psi0, chi_init[b], p.dx)
+            else:
+                # the same formulas over the whole batch at once (numpy); summation order differs from the
+                # reference's nested loops in the last bit
+                dyn = mode_dyn & (goal_close_abs != 0.0)
+                h_lambda = np.where(dyn, h0_all * nb_runs / np.sqrt(np.where(dyn, goal_close_abs, 1.0)), h0_all)
+                per_v = (np.conj(chi_init) * self.psi0).sum(axis=(2, 3)) * self.dx[:, None]     # [B][nb]
+                if kind == "sm":
+                    a0 = np.repeat(per_v.sum(axis=1, keepdims=True), per_v.shape[1], axis=1)
+                elif kind == "re":
+                    a0 = np.full_like(per_v, 0.5)
                 else:
-                    h_lambda[b] = h0
-                a0[b] = _a_value(p.F_type, p.psi0, chi_init[b], p.dx)
+                    a0 = per_v
             pl.set_control(h_lambda, self.nt.astype(np.float64), a0)
             if it == 0:
                 pl.set_E_base(self._pad(base_rows))
             pl.snapshot_load(0)
             self._sweep("iter_%df" % it, FORWARD, (0, 1), 0, eng.FIELD_UT_FWD, 0, self.nt_max + 1, 1, -1,
                         write_E_base=True)
-            E = pl.get_fields()
             gc = pl.goal_overlap(1)
+            if keep_fields:
+                E = pl.get_fields()
+            else:
+                # throughput mode: E_int reduced on the device, functional over the whole batch at once
+                E_int_all = pl.field_integral() * (t_steps * 1e15)
+                tau = gc.sum(axis=1)
+                if kind == "sm":
+                    F_all = -(tau * np.conj(tau)).real
+                elif kind == "re":
+                    F_all = -gc.real.sum(axis=1)
+                else:
+                    F_all = -(gc * np.conj(gc)).real.sum(axis=1)
             stop_all = True
             for b, p in enumerate(self.pbs):
                 if done[b]:
                     continue
-                Et = E[b, :p.nt + 1]
-                E_int = field_integral(Et, p.t_step)
-                F = _F_value(p.F_type, gc[b], p.nb)
+                if keep_fields:
+                    Et = E[b, :p.nt + 1]
+                    E_int = field_integral(Et, p.t_step)
+                    F = _F_value(p.F_type, gc[b], p.nb)
+                    E_list = _shown_fields(Et)
+                else:
+                    E_int, F, E_list = np.complex128(E_int_all[b]), np.complex128(F_all[b]), None
                 J = F.real - h_lambda[b] * h_lambda[b] * E_int.real
                 goal_close_abs[b] = abs(gc[b].sum())
-                E_list = _shown_fields(Et)
                 hist[b].append(IterRow(it, float(goal_close_abs[b]), float(F.real), float(E_int.real), float(J), E_list))
                 if p.q and it >= 1:                       # divergence guard (fitter.py:550-560)
                     if it == p.iter_mid_1:
@@ -527,4 +569,6 @@ class NLevelBatch(_BatchBase):
             if stop_all:
                 break
             it += 1
+        self.ctx.synchronize()
+        self.loop_wall_s = time.perf_counter() - t_loop       # iteration loop only (set-up excluded)
         return hist

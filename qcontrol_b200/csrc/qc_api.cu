@@ -288,6 +288,24 @@ __global__ void instrument_kernel(const cd *psi, const cd *hpsi, const cd *tpsi,
     }
 }
 
+// out[run] = sum_{l=1..nt_run} |E_out[run][l]|^2   (E_int without the dt factor, fitter.py:338-341)
+__global__ void field_integral_kernel(const cd *E_out, const double *ctl, int ctl_stride, int nt_max, double *out) {
+    const int run = blockIdx.x;
+    const int nt = (int)ctl[(long long)ctl_stride * run * 4 + 1];
+    const cd *row = E_out + (long long)run * (nt_max + 1);
+    double acc = 0.0;
+    for (int l = 1 + threadIdx.x; l <= nt; l += blockDim.x) acc += row[l].x * row[l].x + row[l].y * row[l].y;
+    __shared__ double sr[32];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sr[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) t += sr[w];
+        out[run] = t;
+    }
+}
+
 // FP64 FMA throughput: 8 independent chains per thread
 __global__ void fp64_peak_kernel(double *out, int iters, double seed) {
     double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
@@ -901,6 +919,19 @@ extern "C" int32_t qc_get_fields(qc_plan *pl, double *E_out) {
     if (!pl || !E_out) return fail(QC_ERR_ARG, "qc_get_fields: NULL argument");
     QC_CUDA(cudaSetDevice(pl->ctx->device));
     QC_CUDA(cudaMemcpyAsync(E_out, pl->E_out.p, pl->E_out.n * sizeof(cd), cudaMemcpyDeviceToHost, pl->ctx->stream));
+    QC_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+    return QC_OK;
+}
+
+extern "C" int32_t qc_field_integral(qc_plan *pl, double *out) {
+    if (!pl || !out) return fail(QC_ERR_ARG, "qc_field_integral: NULL argument");
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    const qc_plan_desc &d = pl->d;
+    if (pl->instr.n < (size_t)d.batch) QC_CUDA(pl->instr.alloc((size_t)d.batch * 20 * d.nb * d.nlevs));
+    field_integral_kernel<<<d.batch, 128, 0, pl->ctx->stream>>>(pl->E_out.p, pl->ctl.p, pl->ctl_batched, d.nt_max, pl->instr.p);
+    pl->ctx->launches++;
+    QC_CUDA(cudaGetLastError());
+    QC_CUDA(cudaMemcpyAsync(out, pl->instr.p, d.batch * sizeof(double), cudaMemcpyDeviceToHost, pl->ctx->stream));
     QC_CUDA(cudaStreamSynchronize(pl->ctx->stream));
     return QC_OK;
 }

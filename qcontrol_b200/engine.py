@@ -197,6 +197,12 @@ class Plan:
         check(lib.qc_get_fields(self._h, _ptr(out.view(np.float64))))
         return out
 
+    def field_integral(self):
+        """sum_{l>=1} |E_l|^2 per run of the last sweep, reduced on the device."""
+        out = np.empty(self.batch, np.float64)
+        check(lib.qc_field_integral(self._h, _ptr(out)))
+        return out
+
     def get_norms(self):
         out = np.empty((self.batch, self.nb, self.nlevs), np.float64)
         check(lib.qc_get_norms(self._h, _ptr(out)))

@@ -106,6 +106,8 @@ def write_tables(out_path, rows, t_list, nt, imin=-1):
             if r.it < imin:
                 continue
             f.write("{:2d} {:.6f} {:.6f} {:.4f} {:.6f}\n".format(int(r.it), r.goal_close, r.Fsm, r.E_int, r.J))
+            if r.E_tlist is None:          # plotting_flag "tables_iter": no field table (reporter.py:627-630)
+                continue
             for i in range(nt + 1):
                 g.write("{:2d} {:.6f} {:.6e}\n".format(r.it, t_list[i] * 1e+15, abs(r.E_tlist[i])))
 
@@ -143,7 +145,8 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True):
         if tt == "optimal_control_krotov":
             hist = b.run_krotov()
         elif tt == "optimal_control_unit_transform":
-            hist = b.run_unit_transform()
+            tables_iter = str(data_rep.get("fitter", {}).get("plotting_flag", "")).lower() == "tables_iter"
+            hist = b.run_unit_transform(keep_fields=not tables_iter)
         else:
             hist = b.run_prescribed()
         errors = getattr(b, "errors", [""] * len(idxs))

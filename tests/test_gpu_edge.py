@@ -56,10 +56,13 @@ def test_ragged_unit_transform_batch(ctx):
     assert len({p.nt for p in pbs}) == 3
     nb = control.NLevelBatch(pbs, ctx=ctx)
     hist = nb.run_unit_transform()
+    fast = nb.run_unit_transform(keep_fields=False)      # throughput mode: device-side E_int, batched host algebra
     for b, pb in enumerate(pbs):
         want = _rows(qo.Fitter(pb).run())
         got = _rows(hist[b])
         assert got.shape == want.shape and np.allclose(got[1:], want[1:], rtol=1e-8, atol=0), (b, got - want)
+        assert np.allclose(_rows(fast[b])[1:], want[1:], rtol=1e-8, atol=0)
+        assert fast[b][-1].E_tlist is None and hist[b][-1].E_tlist is not None
     nb.close()
 
 

@@ -35,7 +35,7 @@ def template(iters):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--iters", type=int, default=12)
     ap.add_argument("--copies", type=int, nargs="+", default=[1, 20])
     a = ap.parse_args()
     from qcontrol_b200 import batch, config, control, engine, newcheb, task_manager
@@ -51,22 +51,25 @@ def main():
         pbs.append(newcheb.problem_from(c, tm))
     for copies in a.copies:
         runs = pbs * copies
-        t0 = time.perf_counter()
         nb = control.NLevelBatch(runs, ctx=ctx)
-        nb.run_unit_transform(iter_max=0)            # set-up + one iteration (tables, uploads, first sweeps)
-        ctx.synchronize()
-        setup_s = time.perf_counter() - t0
-        nb.time_sweeps, nb.sweep_ms = True, 0.0
-        t0 = time.perf_counter()
-        hist = nb.run_unit_transform()
-        ctx.synchronize()
-        wall = time.perf_counter() - t0
-        iters = len(hist[0]) - 1
-        steps = sum(p.nt for p in runs) * 2 * iters * runs[0].nb          # solver steps (per basis vector)
-        traj_bytes = sum(p.nt for p in runs) * iters * 2 * runs[0].nb * runs[0].nlevs * 16
-        print(json.dumps({"workload": "ut_jx_Tsweep x%d" % copies, "runs": len(runs), "iterations_per_run": iters,
-                          "wall_s": wall, "sweep_kernels_s": nb.sweep_ms * 1e-3, "first_call_incl_setup_s": setup_s, "ut_iterations_per_s": len(runs) * iters / wall,
-                          "solver_steps_per_s": steps / wall, "traj_hbm_gbs_algorithmic": traj_bytes / wall / 1e9,
+        walls = {}
+        for n_it in (2, a.iters):                      # set-up cost is paid by both calls: the difference is the loop
+            nb.time_sweeps, nb.sweep_ms = True, 0.0
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            hist = nb.run_unit_transform(iter_max=n_it - 1, keep_fields=False)
+            ctx.synchronize()
+            walls[n_it] = (nb.loop_wall_s, nb.sweep_ms * 1e-3, time.perf_counter() - t0)
+        d_it = a.iters - 2
+        d_wall = walls[a.iters][0] - walls[2][0]
+        d_sweep = walls[a.iters][1] - walls[2][1]
+        steps = sum(p.nt for p in runs) * 2 * d_it * runs[0].nb          # solver steps (per basis vector)
+        traj_bytes = sum(p.nt for p in runs) * d_it * 2 * runs[0].nb * runs[0].nlevs * 16
+        print(json.dumps({"workload": "ut_jx_Tsweep x%d" % copies, "runs": len(runs), "iterations_timed": d_it,
+                          "setup_s": walls[2][2] - walls[2][0], "wall_s_per_iteration": d_wall / d_it,
+                          "sweep_kernels_s_per_iteration": d_sweep / d_it,
+                          "ut_iterations_per_s": len(runs) * d_it / d_wall,
+                          "solver_steps_per_s": steps / d_wall, "traj_hbm_gbs_algorithmic": traj_bytes / d_wall / 1e9,
                           "nt_range": [min(p.nt for p in runs), max(p.nt for p in runs)], "launches": ctx.launches}))
         nb.close()
     ctx.close()
