@@ -228,8 +228,15 @@ def run_gpu_arm(a):
         achieved = flops_launch / kdur / 1e12
         peak_nominal = 148 * 64 * 2 * 1.965e9 / 1e12
         peak_meas = ctx.fp64_peak_tflops()
+        traffic = traffic_src = None
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_grid_sweep.json")
+        if os.path.exists(tpath):         # DRAM bytes of this kernel from the committed ncu capture, scaled per (run, step)
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic = tj["dram_bytes_per_run_step"] * B * nt
+            traffic_src = tj["source"]
         roof = {"bound": "fp64", "achieved": achieved, "peak": peak_meas, "unit": "TFLOP/s", "frac": achieved / peak_meas,
-                "traffic": None, "peak_source": "measured here: qc_measure_fp64_peak (DFMA chains, burst); MEASURED_PEAKS.json has no FP64 entry",
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": "measured here: qc_measure_fp64_peak (DFMA chains, burst); MEASURED_PEAKS.json has no FP64 entry",
                 "peak_nominal": peak_nominal, "kernel": "grid_sweep_kernel<11> (Krotov forward sweep)",
                 "kernel_ms_per_launch": kdur * 1e3, "flops_per_launch": flops_launch,
                 "hbm_algorithmic_bytes_per_launch": (32 * NP_ + 16) * B * nt,
