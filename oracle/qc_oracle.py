@@ -265,6 +265,9 @@ class Problem:
     q: float = 0.0
     impulses_number: int = 2
     delay: float = 600e-15
+    k_E: float = 1e29               # local control: spring constant of the field / multiplier ODE [1/s^2]
+    lamb: float = 4e14              # local control: decay rate [1/s]
+    pow_: float = 0.8               # local control: exponent of the decay term
     F_type: str = "sm"
     F_goal: float = -1.0
     init_dir: int = FORWARD
@@ -591,9 +594,10 @@ class IterRow:
 
 
 class Fitter:
-    """Restatement of FittingSolver for the task types on the hot path
-    (single_pot, filtering, trans_wo_control, intuitive_control,
-    optimal_control_krotov, optimal_control_unit_transform).
+    """Restatement of FittingSolver for every task type (single_pot,
+    filtering, trans_wo_control, intuitive_control, local_control_population,
+    local_control_projection, optimal_control_krotov,
+    optimal_control_unit_transform).
     ``on_step(prop_id, vect, stepper)`` is called after every solver step
     (where the reference calls reporter.print_time_point_prop)."""
 
@@ -613,10 +617,24 @@ class Fitter:
             patched = pb.laser_field(pb.E0, st.t, pb.t0, pb.sigma) * \
                 pb.laser_field_hf(st.freq_mult, st.t, pb.pcos, pb.w_list)
         tt = pb.task_type
+        self.E_patched = patched
         if tt == "intuitive_control":
             for k in range(1, pb.impulses_number):
                 patched += pb.laser_field(pb.E0, st.t, pb.t0 + k * pb.delay, pb.sigma)
+            self.E_patched = patched
             return patched
+        if tt == "local_control_population":              # fitter.py:673-692
+            if st.E == 0.0:
+                st.E = self.E_patched
+            if self.E_patched <= 0:
+                raise RuntimeError("E_patched has to be positive")
+            if st.E <= 0:
+                raise RuntimeError("E has to be positive")
+            first = st.E - self.E_patched
+            second = self.E_vel * math.pow(self.E_patched / st.E, pb.pow_)
+            E_acc = -pb.k_E * first - pb.lamb * second
+            self.E_vel += E_acc * abs(st.dt)
+            return st.E + self.E_vel * abs(st.dt)
         if tt == "optimal_control_krotov":
             if self.iter_step == 0:
                 return patched
@@ -659,6 +677,57 @@ class Fitter:
             return self.E_tlist[-1] if st.l == 0 else self.E_tlist[-st.l]
         return pb.laser_field(pb.E0, st.t, pb.t0, pb.sigma)
 
+    def _freq_mult(self, st: Stepper):
+        """fitter.py:814-836"""
+        pb = self.pb
+        if pb.task_type == "local_control_projection":
+            if self.fm_patched < 0:
+                raise RuntimeError("freq_mult_patched has to be positive or zero")
+            if st.freq_mult < 0:
+                raise RuntimeError("Frequency multiplier has to be positive or zero")
+            first = st.freq_mult - self.fm_patched
+            second = self.fm_vel * math.pow(self.fm_patched / st.freq_mult, pb.pow_)
+            acc = -pb.k_E * first - pb.lamb * second
+            self.fm_vel += acc * abs(st.dt)
+            return np.float64(st.freq_mult + self.fm_vel * abs(st.dt))
+        return np.float64(self.fm_patched)
+
+    def _feedback(self, st: Stepper):
+        """do_the_thing, fitter.py:578-623 (the state it leaves behind; no printing)."""
+        pb = self.pb
+        r = st.rec
+        if pb.task_type == "local_control_population":
+            coef = 2.0 * CM_TO_ERG / RED_PLANCK_H
+            dAdt = st.E * r.psigc_psie.imag * coef
+            if dAdt >= 0.0:
+                self.dAdt_happy = dAdt
+            elif abs(r.psigc_psie.imag) > pb.epsilon:
+                self.E_patched = -self.dAdt_happy / (r.psigc_psie.imag * coef)
+            else:
+                self.E_patched = self.dAdt_happy / (pb.epsilon * coef)
+            self.dAdt = dAdt
+        elif pb.task_type == "local_control_projection":
+            coef2 = -4.0 * CM_TO_ERG / RED_PLANCK_H
+            Sge2 = r.psigc_psie * r.psigc_psie
+            Sdvge = r.psigc_psie * r.psigc_dv_psie
+            freq_cm = HZ_TO_CM * pb.nu_L
+            body = Sdvge + freq_cm * st.freq_mult * Sge2
+            dAdt = body.imag * coef2
+            if dAdt >= 0.0:
+                self.dAdt_happy = dAdt
+            else:
+                if Sge2.imag > pb.epsilon:
+                    self.fm_patched = (self.dAdt_happy - coef2 * Sdvge.imag) / (Sge2.imag * freq_cm * coef2)
+                elif Sge2.imag > 0.0:
+                    self.fm_patched = (self.dAdt_happy - coef2 * Sdvge.imag) / (pb.epsilon * freq_cm * coef2)
+                elif Sge2.imag < -pb.epsilon:
+                    self.fm_patched = -Sdvge.imag / (Sge2.imag * freq_cm)
+                else:
+                    self.fm_patched = Sdvge.imag / (pb.epsilon * freq_cm)
+                if self.fm_patched < 0.0:
+                    self.fm_patched = np.float64(0.0)
+            self.dAdt = dAdt
+
     # -- one sweep ---------------------------------------- fitter.py:213-422
     def _sweep(self, direction, chiT):
         pb = self.pb
@@ -683,7 +752,7 @@ class Fitter:
             init, fin = chiT, pb.psi0
             t_init = pb.T
         prop_id = "iter_%d%s" % (self.iter_step, tag)
-        solvers = [Stepper(pb, cb, instrument=self.instrument) for _ in range(nb)]
+        solvers = [Stepper(pb, cb, freq_cb=self._freq_mult, instrument=self.instrument) for _ in range(nb)]
         for v in range(nb):
             solvers[v].start(init[v], fin[v], direction)
         E_new = [solvers[0].E] if direction == FORWARD else []
@@ -697,6 +766,7 @@ class Fitter:
                 new[v] = solvers[v].psi_omega if pb.hf_hide else solvers[v].psi
                 if self.on_step:
                     self.on_step(prop_id, v, solvers[v])
+                self._feedback(solvers[v])
             if direction == BACKWARD:
                 self.chi_cur = new
                 self.chi_tlist.append(new)
@@ -780,6 +850,11 @@ class Fitter:
         self.E_int = np.float64(0.0)
         self.chi_tlist = []
         self.psi_tlist = []
+        self.E_vel = np.float64(0.0)                      # FitterDynamicState, fitter.py:22-31
+        self.fm_vel = np.float64(0.0)
+        self.E_patched = np.float64(0.0)
+        self.fm_patched = np.float64(1.0)
+        self.dAdt_happy = np.float64(0.0)
         optimal = pb.task_type in ("optimal_control_krotov", "optimal_control_unit_transform")
         if pb.task_type == "optimal_control_unit_transform":
             gc0 = np.zeros(pb.nb, np.complex128)
@@ -1016,5 +1091,6 @@ def make_problem(user: dict, apply_auto: bool = False) -> Problem:
         w_list=list(f["w_list"]), hf_hide=bool(f["hf_hide"]), h_lambda=f["h_lambda"],
         h_lambda_mode=f["h_lambda_mode"].lower(), epsilon=f["epsilon"], iter_max=int(f["iter_max"]),
         iter_mid_1=int(f["iter_mid_1"]), iter_mid_2=int(f["iter_mid_2"]), q=f["q"],
-        impulses_number=int(f["impulses_number"]), delay=f["delay"], F_type=f["F_type"].lower(),
+        impulses_number=int(f["impulses_number"]), delay=f["delay"], k_E=f["k_E"], lamb=f["lamb"],
+        pow_=f["pow"], F_type=f["F_type"].lower(),
         F_goal=F_goal, init_dir=init_dir, t_step=t_step, t_list=t_list)

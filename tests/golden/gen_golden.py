@@ -125,6 +125,20 @@ def conf_krotov(nt, iter_max, np_=1024):
                                        "nu_L": 0.29297e15}}}
 
 
+def conf_local(task, nt, k_E, lamb, pw, E0mult, np_=256, nt_pulse=None):
+    """Local-control tasks (tests/functional_tests.py:508-661) at the shipped time step (450 fs / 315000) with
+    the pulse compressed to ``nt_pulse`` steps and amplified, and a stiffer field / multiplier ODE, so that the
+    feedback branches of fitter.py:598-623 fire within a few hundred steps."""
+    dt = 450e-15 / 315000
+    T, Tp = dt * nt, dt * (nt_pulse or nt)
+    return {"task_type": task, "pot_type": "morse", "wf_type": "morse", "hamil_type": "ntriv",
+            "init_guess": "gauss", "init_guess_hf": "exp", "nb": 1, "nlevs": 2, "T": T, "L": 5.0, "np": np_,
+            "a": 1.0, "De": 20000.0, "x0p": -0.17, "a_e": 1.0, "De_e": 10000.0, "Du": 20000.0,
+            "fitter": {"k_E": k_E, "lamb": lamb, "pow": pw, "epsilon": 1e-15, "impulses_number": 1, "mod_log": 500,
+                       "propagation": {"m": 0.5, "nch": 64, "nt": nt, "E0": 71.54 * E0mult, "t0": Tp / 2,
+                                       "sigma": Tp / 6, "nu_L": 0.29297e15}}}
+
+
 def conf_ut_jx(nt, iter_max, nlevs=2, w_list=(1.5, -1.0, 0.7999999999999998), T=5.4e-13):
     return {"task_type": "optimal_control_unit_transform", "pot_type": "none", "wf_type": "const",
             "hamil_type": "BH_model", "lf_aug_type": "x", "init_guess": "sqrsin", "init_guess_hf": "sin_set",
@@ -274,7 +288,7 @@ def pack_fitter(rep, fs, tm, err="", keep_psi=()):
         out[key + "__E"] = np.array([r["E"] for r in rows])
         out[key + "__psi"] = np.stack([r["psi"] for r in rows])
         for f in ("ener", "norm", "overlp0", "overlpf", "momx", "momx2", "momp", "momp2", "psi_max_abs",
-                  "psi_max_real", "smoms"):
+                  "psi_max_real", "smoms", "freq_mult"):
             out[key + "__" + f] = np.stack([np.asarray(r[f]) for r in rows])
     return out
 
@@ -377,6 +391,28 @@ def case_fitter_grid(R):
         save(name, **out)
 
 
+def case_fitter_local(R):
+    """Local control (population: Euler ODE for the field; projection: fed-back carrier-frequency multiplier,
+    which makes eL, the energy window and the Newton table change every step).  The projection runs stop at step
+    900 of a 1200-step pulse: beyond that the REFERENCE itself amplifies a 3e-16 perturbation of psi0 to 1e-8
+    (the feedback divides by a vanishing Im(S^2)), before it the sensitivity stays below 1e-13."""
+    for name, user, every in (
+            ("fit_loc_pop_256", conf_local("local_control_population", 600, 2e33, 1e17, 0.8, 40.0), 1),
+            ("fit_loc_proj_256", conf_local("local_control_projection", 900, 2e33, 2e16, 0.65, 300.0, nt_pulse=1200), 1),
+            ("fit_loc_proj_1024", conf_local("local_control_projection", 900, 2e33, 2e16, 0.65, 300.0, np_=1024,
+                                             nt_pulse=1200), 50)):
+        conf, tm, fs, rep, err = run_fitter(R, user, every)
+        out = pack_fitter(rep, fs, tm, err, ("iter_0f/basis_0",))
+        if every == 1:                       # every step's E and multiplier, wavefunctions only every 50 steps
+            k = "iter_0f__basis_0__"
+            keep = np.arange(len(out[k + "l"])) % 50 == 0
+            keep[-1] = True
+            out[k + "psi_l"] = out[k + "l"][keep]
+            out[k + "psi"] = out[k + "psi"][keep]
+        out["conf_json"] = np.array(repr(user))
+        save(name, **out)
+
+
 def case_fitter_nlevel(R):
     """Unitary-transformation control on N-level systems (np = 1)."""
     def pi_patch(conf, tm, kw):            # tests/functional_tests.py:29-75
@@ -455,7 +491,7 @@ def case_shipped(R):
 
 
 CASES = {"kat": case_kat, "one_step": case_one_step, "fitter_grid": case_fitter_grid,
-         "fitter_nlevel": case_fitter_nlevel, "shipped": case_shipped}
+         "fitter_nlevel": case_fitter_nlevel, "fitter_local": case_fitter_local, "shipped": case_shipped}
 
 if __name__ == "__main__":
     R = load_reference()
