@@ -55,8 +55,12 @@ typedef enum {
                                   intuitive_control, Krotov iteration 0 forward, UT backward)            */
     QC_FIELD_KROTOV_FWD = 1,   /* E = -2 Im<chi_old[nt-l].f[1] | psi_w.f[0]> / h_lambda   (fitter.py:700-706) */
     QC_FIELD_KROTOV_BWD = 2,   /* E = -2 Im<chi_w.f[1] | psi_old[nt-l].f[0]> / h_lambda   (fitter.py:791-796) */
-    QC_FIELD_UT_FWD = 3        /* E = E_base[l] - s[l] Im(sum_v a0[v] <chi[-l]|psi_cur>) / h_lambda
+    QC_FIELD_UT_FWD = 3,       /* E = E_base[l] - s[l] Im(sum_v a0[v] <chi[-l]|psi_cur>) / h_lambda
                                   (fitter.py:739-778)                                                     */
+    QC_FIELD_LOCAL_PROJ = 4    /* local_control_projection: E[l] supplied; the carrier-frequency multiplier
+                                  follows its ODE towards the value fed back from the previous step, so eL,
+                                  exp_L, the energy window and the Newton table are rebuilt on the device
+                                  every step (fitter.py:598-623, 814-836; propagation.py:379-407)         */
 } qc_field_mode;
 
 typedef struct qc_context qc_context;
@@ -170,6 +174,21 @@ int32_t qc_set_instr_grid(qc_plan *plan, const double *x, const double *akx_re);
  * two_m = 2*m; psi0_slot / psif_slot: snapshot slots of psi0 / psif (-1 to skip). */
 int32_t qc_instrument(qc_plan *plan, const double *E_full, double two_m, int32_t psi0_slot, int32_t psif_slot,
                       double *out);
+
+/* Local control with a fed-back frequency multiplier (grid plans with hf_hide, QC_FIELD_LOCAL_PROJ sweeps).
+ * params[batch][12] = the four energy extremes of propagation.py:371-375 (v0[0]+|akx2[np/2-1]|, vmin0,
+ * v1[0]+|akx2[np/2-1]|, vmin1), E0, nu_L, carrier frequency nu, k_E, lamb, pow, epsilon, signed dt;
+ * t_tab[batch][nt_max+1] = the step times t_l; xp[nch] = the interpolation nodes (math_base.py:166-170).
+ * Resets the state of FitterDynamicState (fitter.py:22-31): freq_mult = freq_mult_patched = 1, velocities 0.
+ * The multiplier used at step l is returned in the imaginary slot of E_out[run][l] (qc_get_fields). */
+int32_t qc_set_local_control(qc_plan *plan, const double *params, const double *t_tab, const double *xp);
+/* out[batch][11] = freq_mult, freq_mult_vel, freq_mult_patched, dAdt_happy, error (0 ok, 1 "freq_mult_patched
+ * has to be positive or zero", 2 "Frequency multiplier has to be positive or zero": the run stopped there, like
+ * the RuntimeError of fitter.py:817-821), psigc_psie (2), psigc_dv_psie (2), dA/dt of the last step, error step. */
+int32_t qc_get_local_state(qc_plan *plan, double *out);
+/* Overwrite the feedback state: state[batch][4] = freq_mult, freq_mult_vel, freq_mult_patched, dAdt_happy
+ * (restart of a run from a stored time step; FitterDynamicState.from_json, fitter.py:33-50). */
+int32_t qc_set_local_state(qc_plan *plan, const double *state);
 
 /* Field used at each step of the last sweep(s): E_out[batch][nt_max+1] complex (E_tlist, fitter.py:281,326). */
 int32_t qc_get_fields(qc_plan *plan, double *E_out);

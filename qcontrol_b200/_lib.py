@@ -18,7 +18,7 @@ SYMBOLS = (
     "qc_abi_version", "qc_last_error", "qc_create", "qc_destroy", "qc_synchronize", "qc_timer_start",
     "qc_timer_stop", "qc_launch_count", "qc_measure_fp64_peak", "qc_plan_create", "qc_plan_destroy",
     "qc_set_static", "qc_set_poly", "qc_set_state", "qc_get_state", "qc_set_step_scalars", "qc_set_control",
-    "qc_sweep", "qc_prop_step", "qc_apply_hamil", "qc_set_instr_grid", "qc_instrument", "qc_get_fields", "qc_field_integral", "qc_get_norms", "qc_snapshot_set", "qc_snapshot_load", "qc_goal_overlap", "qc_krotov_terminal",
+    "qc_sweep", "qc_prop_step", "qc_apply_hamil", "qc_set_instr_grid", "qc_instrument", "qc_set_local_control", "qc_get_local_state", "qc_set_local_state", "qc_get_fields", "qc_field_integral", "qc_get_norms", "qc_snapshot_set", "qc_snapshot_load", "qc_goal_overlap", "qc_krotov_terminal",
     "qc_get_traj", "qc_record_state", "qc_propagate_host",
 )
 
@@ -72,6 +72,9 @@ def _load():
         "qc_apply_hamil": (i32, [vp, i32, i32, dp, C.c_double, dp]),
         "qc_set_instr_grid": (i32, [vp, dp, dp]),
         "qc_instrument": (i32, [vp, dp, C.c_double, i32, i32, dp]),
+        "qc_set_local_control": (i32, [vp, dp, dp, dp]),
+        "qc_get_local_state": (i32, [vp, dp]),
+        "qc_set_local_state": (i32, [vp, dp]),
         "qc_get_fields": (i32, [vp, dp]),
         "qc_field_integral": (i32, [vp, dp]),
         "qc_get_norms": (i32, [vp, dp]),

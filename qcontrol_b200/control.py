@@ -318,6 +318,10 @@ class GridBatch(_BatchBase):
     def _finish_forward(self, it, E0_start):
         pl = self.plan
         E = pl.get_fields()
+        if self.pbs[0].task_type == "local_control_projection":
+            self.freq_mult = np.ascontiguousarray(E.imag)      # the multiplier rides in the imaginary slot
+            self.freq_mult[:, 0] = 1.0
+            E = E.real.astype(np.complex128)
         gc = pl.goal_overlap(1)
         rows = []
         for b, p in enumerate(self.pbs):
@@ -340,6 +344,75 @@ class GridBatch(_BatchBase):
         self._sweep("iter_0f", FORWARD, (0, 1), 0, eng.FIELD_PRESCRIBED, 1, self.nt_max, -1, -1)
         E0s = [self._prescribed_field(p, FORWARD)[0] for p in self.pbs]
         rows, _ = self._finish_forward(0, E0s)
+        return [[r] for r in rows]
+
+    def _local_population_field(self, p):
+        """E_l of local_control_population: Euler steps of the field ODE towards the envelope
+        (fitter.py:673-692).  The value patched in by do_the_thing (fitter.py:592-595) is overwritten by the
+        envelope at the next step (fitter.py:653-658) before anyone reads it, so the field does not depend on
+        the state and is integrated here, with the reference's scalar expressions."""
+        adt = abs(p.t_step)
+        E_vel = np.float64(0.0)
+        E = np.float64(0.0)
+        out = []
+        for t in step_times(p, FORWARD):
+            if p.hf_hide:
+                patched = p.laser_field(p.E0, t, p.t0, p.sigma)
+            else:
+                patched = p.laser_field(p.E0, t, p.t0, p.sigma) * p.laser_field_hf(np.float64(1.0), t, p.pcos, p.w_list)
+            if E == 0.0:
+                E = patched
+            if patched <= 0:
+                raise RuntimeError("E_patched has to be positive")
+            if E <= 0:
+                raise RuntimeError("E has to be positive")
+            first = E - patched
+            second = E_vel * math.pow(patched / E, p.pow_)
+            E_acc = -p.k_E * first - p.lamb * second
+            E_vel += E_acc * adt
+            E = E + E_vel * adt
+            out.append(E)
+        return out
+
+    def run_local_population(self):
+        """local_control_population (fitter.py:425-438 with the field of fitter.py:673-692)."""
+        self.goal_close_scal = np.zeros(self.B, np.complex128)
+        pl = self.plan
+        fields = [self._local_population_field(p) for p in self.pbs]
+        pl.snapshot_load(0)
+        pl.set_E_base(self._pad(fields))
+        self._sweep("iter_0f", FORWARD, (0, 1), 0, eng.FIELD_PRESCRIBED, 1, self.nt_max, -1, -1)
+        rows, _ = self._finish_forward(0, [f[0] for f in fields])
+        return [[r] for r in rows]
+
+    _LOCAL_ERRORS = {1: "freq_mult_patched has to be positive or zero",
+                     2: "Frequency multiplier has to be positive or zero"}
+
+    def run_local_projection(self):
+        """local_control_projection: prescribed envelope, carrier-frequency multiplier fed back from
+        <psi_e|psi_g> and <psi_e|v_g - v_e|psi_g> of the previous step (fitter.py:598-623, 814-836).  The ODE of
+        the multiplier, the energy window and the Newton table of every step are evaluated inside the sweep
+        kernel; ``self.freq_mult[run][l]`` holds the multipliers afterwards."""
+        p0 = self.pbs[0]
+        if not p0.hf_hide or getattr(p0, "carrier", "exp") != "exp":
+            raise NotImplementedError("local_control_projection runs in the rotating frame (hf_hide) with the 'exp' "
+                                      "carrier; without hf_hide the reference never updates the multiplier")
+        self.goal_close_scal = np.zeros(self.B, np.complex128)
+        pl = self.plan
+        params = np.zeros((self.B, 12))
+        for b, p in enumerate(self.pbs):
+            kmax = abs(p.akx2[int(p.np_ / 2 - 1)])
+            params[b] = [p.v[0][0] + kmax, p.vmin[0], p.v[1][0] + kmax, p.vmin[1], p.E0, p.nu_L,
+                         getattr(p, "nu", p.nu_L), p.k_E, p.lamb, p.pow_, p.epsilon, p.t_step]
+        xp = math_base.newton_table(p0.nch, 1.0)[0]
+        pl.set_local_control(params, self._pad([step_times(p, FORWARD) for p in self.pbs], np.float64), xp)
+        pl.snapshot_load(0)
+        fields = [self._prescribed_field(p, FORWARD) for p in self.pbs]
+        pl.set_E_base(self._pad(fields))
+        self._sweep("iter_0f", FORWARD, (0, 1), 0, eng.FIELD_LOCAL_PROJ, 1, self.nt_max, -1, -1)
+        self.local_state = pl.get_local_state()
+        self.errors = [self._LOCAL_ERRORS.get(int(c), "") for c in self.local_state[:, 4]]
+        rows, _ = self._finish_forward(0, [f[0] for f in fields])
         return [[r] for r in rows]
 
     def run_krotov(self, iter_max=None):

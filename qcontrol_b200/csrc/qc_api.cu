@@ -109,6 +109,8 @@ struct qc_plan {
     PolySlot poly[3];                 // slot 2: internal identity polynomial (one bare H application)
     DevBuf<cd> work[4];               // psi backup, H psi, T psi, P psi (instrumentation)
     DevBuf<double> zero_v, akx, xgrid, instr;
+    DevBuf<double> lc, lc_t, lc_rt, lc_rdiag;     // local control (qc_set_local_control)
+    bool lc_set = false;
 };
 
 // ---------------------------------------------------------------------------
@@ -578,6 +580,7 @@ extern "C" int32_t qc_plan_destroy(qc_plan *pl) {
     for (auto &s : pl->poly) { s.xp.release(); s.sc.release(); s.dv.release(); }
     for (auto &b : pl->work) b.release();
     pl->zero_v.release(); pl->akx.release(); pl->xgrid.release(); pl->instr.release();
+    pl->lc.release(); pl->lc_t.release(); pl->lc_rt.release(); pl->lc_rdiag.release();
     qc_context *ctx = pl->ctx;
     delete pl;
     if (--ctx->live_plans == 0 && ctx->released) context_free(ctx);
@@ -683,17 +686,17 @@ extern "C" int32_t qc_set_control(qc_plan *pl, const double *ctl, int32_t batche
 // ---------------------------------------------------------------------------
 // sweeps
 // ---------------------------------------------------------------------------
-template <int LOG2N>
+template <int LOG2N, bool LOCAL = false>
 static int32_t launch_grid(qc_plan *pl, const qc::GridParams &gp, cudaStream_t stream) {
     typedef qc::GridCfg<LOG2N> C;
     static bool attr_done[64] = {false};
     const int dev = pl->ctx->device;
     if (!attr_done[dev & 63]) {
-        QC_CUDA(cudaFuncSetAttribute(qc::grid_sweep_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        QC_CUDA(cudaFuncSetAttribute(qc::grid_sweep_kernel<LOG2N, LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)C::SMEM_BYTES));
         attr_done[dev & 63] = true;
     }
-    qc::grid_sweep_kernel<LOG2N><<<gp.run_count, C::NTHREADS, C::SMEM_BYTES, stream>>>(gp);
+    qc::grid_sweep_kernel<LOG2N, LOCAL><<<gp.run_count, C::NTHREADS, C::SMEM_BYTES, stream>>>(gp);
     pl->ctx->launches++;
     QC_CUDA(cudaGetLastError());
     return QC_OK;
@@ -727,7 +730,10 @@ static int32_t run_sweep(qc_plan *pl, const qc_sweep_args *a, bool single_step, 
     if (a->nsteps < 1 || a->l_first < 0 || a->l_first > d.nt_max)
         return fail(QC_ERR_ARG, "qc_sweep: l_first=%d nsteps=%d (nt_max=%d)", a->l_first, a->nsteps, d.nt_max);
     const int mode = a->field_mode;
-    if (mode < 0 || mode > 3) return fail(QC_ERR_ARG, "qc_sweep: field_mode %d", mode);
+    if (mode < 0 || mode > 4) return fail(QC_ERR_ARG, "qc_sweep: field_mode %d", mode);
+    const bool local = mode == QC_FIELD_LOCAL_PROJ;
+    if (local && (!pl->grid || !d.hf_hide || single_step || !pl->lc_set))
+        return fail(QC_ERR_STATE, "qc_sweep: QC_FIELD_LOCAL_PROJ needs a grid plan with hf_hide and qc_set_local_control");
     if (pl->grid && mode == QC_FIELD_UT_FWD) return fail(QC_ERR_ARG, "qc_sweep: UT field update needs an N-level plan (newcheb.py:887-889)");
     if (!pl->grid && (mode == QC_FIELD_KROTOV_FWD || mode == QC_FIELD_KROTOV_BWD))
         return fail(QC_ERR_ARG, "qc_sweep: Krotov field update needs a grid plan");
@@ -735,9 +741,9 @@ static int32_t run_sweep(qc_plan *pl, const qc_sweep_args *a, bool single_step, 
         return fail(QC_ERR_ARG, "qc_sweep: traj_read=%d traj_write=%d", a->traj_read, a->traj_write);
     if ((a->traj_read >= 0 || a->traj_write >= 0) && !d.store_traj)
         return fail(QC_ERR_STATE, "qc_sweep: plan was created without trajectory buffers");
-    if (mode != QC_FIELD_PRESCRIBED && a->traj_read < 0)
+    if (mode != QC_FIELD_PRESCRIBED && !local && a->traj_read < 0)
         return fail(QC_ERR_ARG, "qc_sweep: field mode %d reads the previous sweep; traj_read must be 0 or 1", mode);
-    if (d.hf_hide && !single_step && !pl->expL[a->poly_slot].p) return fail(QC_ERR_STATE, "qc_sweep: exp_L table (qc_set_step_scalars which=1) missing");
+    if (d.hf_hide && !single_step && !local && !pl->expL[a->poly_slot].p) return fail(QC_ERR_STATE, "qc_sweep: exp_L table (qc_set_step_scalars which=1) missing");
     if (mode == QC_FIELD_UT_FWD && !pl->s_env.p) return fail(QC_ERR_STATE, "qc_sweep: s_env table (qc_set_step_scalars which=2) missing");
     QC_CUDA(cudaSetDevice(pl->ctx->device));
     const PolySlot &ps = pl->poly[a->poly_slot];
@@ -759,6 +765,16 @@ static int32_t run_sweep(qc_plan *pl, const qc_sweep_args *a, bool single_step, 
         g.traj_in = a->traj_read >= 0 ? pl->traj[a->traj_read].p : nullptr;
         g.traj_out = a->traj_write >= 0 ? pl->traj[a->traj_write].p : nullptr;
         g.norms = pl->norms.p;
+        g.lc = pl->lc.p; g.lc_t = pl->lc_t.p; g.lc_rt = pl->lc_rt.p; g.lc_rdiag = pl->lc_rdiag.p;
+        if (local) {
+            switch (pl->log2n) {
+                case 8: return launch_grid<8, true>(pl, g, lst);
+                case 9: return launch_grid<9, true>(pl, g, lst);
+                case 10: return launch_grid<10, true>(pl, g, lst);
+                case 11: return launch_grid<11, true>(pl, g, lst);
+            }
+            return fail(QC_ERR_ARG, "qc_sweep: unsupported np");
+        }
         switch (pl->log2n) {
             case 8: return launch_grid<8>(pl, g, lst);
             case 9: return launch_grid<9>(pl, g, lst);
@@ -912,6 +928,61 @@ extern "C" int32_t qc_instrument(qc_plan *pl, const double *E_full, double two_m
     QC_CUDA(cudaGetLastError());
     QC_CUDA(cudaMemcpyAsync(out, pl->instr.p, items * 20 * sizeof(double), cudaMemcpyDeviceToHost, st));
     QC_CUDA(cudaStreamSynchronize(st));
+    return QC_OK;
+}
+
+extern "C" int32_t qc_set_local_control(qc_plan *pl, const double *params, const double *t_tab, const double *xp) {
+    if (!pl || !params || !t_tab || !xp) return fail(QC_ERR_ARG, "qc_set_local_control: NULL argument");
+    if (!pl->grid || !pl->d.hf_hide) return fail(QC_ERR_STATE, "qc_set_local_control: needs a grid plan with hf_hide");
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    const int nch = pl->d.nch, B = pl->d.batch;
+    std::vector<double> lc((size_t)B * qc::LC_STRIDE, 0.0);
+    for (int b = 0; b < B; ++b) {
+        double *r = &lc[(size_t)b * qc::LC_STRIDE];
+        r[qc::LC_FM] = 1.0;                                 // FitterDynamicState, fitter.py:22-31
+        r[qc::LC_PATCHED] = 1.0;
+        const double *q = params + (size_t)b * 12;
+        for (int k = 0; k < 4; ++k) r[qc::LC_EXTR0 + k] = q[k];
+        r[qc::LC_E0] = q[4]; r[qc::LC_NUL] = q[5]; r[qc::LC_NU] = q[6]; r[qc::LC_KE] = q[7]; r[qc::LC_LAMB] = q[8];
+        r[qc::LC_POW] = q[9]; r[qc::LC_EPS] = q[10]; r[qc::LC_DT] = q[11];
+        if (q[11] == 0.0) return fail(QC_ERR_ARG, "qc_set_local_control: dt of row %d is zero", b);
+    }
+    // partial products of the Newton table (math_base.py:176-186), transposed: rt[j][i] = prod_{m<=j} (xp_i - xp_m)
+    std::vector<double> rt((size_t)nch * nch, 0.0), rdiag(nch, 0.0);
+    for (int i = 1; i < nch; ++i) {
+        double res = 1.0;
+        for (int j = 0; j < i; ++j) {
+            res *= (xp[i] - xp[j]);
+            rt[(size_t)j * nch + i] = res;
+        }
+        rdiag[i] = 1.0 / res;
+    }
+    int32_t rc = upload(pl, pl->lc, lc.data(), lc.size());
+    if (!rc) rc = upload(pl, pl->lc_t, t_tab, (size_t)B * (pl->d.nt_max + 1));
+    if (!rc) rc = upload(pl, pl->lc_rt, rt.data(), rt.size());
+    if (!rc) rc = upload(pl, pl->lc_rdiag, rdiag.data(), rdiag.size());
+    if (rc) return rc;
+    pl->lc_set = true;
+    return QC_OK;
+}
+
+extern "C" int32_t qc_get_local_state(qc_plan *pl, double *out) {
+    if (!pl || !out) return fail(QC_ERR_ARG, "qc_get_local_state: NULL argument");
+    if (!pl->lc_set) return fail(QC_ERR_STATE, "qc_get_local_state: qc_set_local_control has not been called");
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    QC_CUDA(cudaMemcpy2DAsync(out, qc::LC_NSTATE * sizeof(double), pl->lc.p, qc::LC_STRIDE * sizeof(double),
+                              qc::LC_NSTATE * sizeof(double), pl->d.batch, cudaMemcpyDeviceToHost, pl->ctx->stream));
+    QC_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+    return QC_OK;
+}
+
+extern "C" int32_t qc_set_local_state(qc_plan *pl, const double *state) {
+    if (!pl || !state) return fail(QC_ERR_ARG, "qc_set_local_state: NULL argument");
+    if (!pl->lc_set) return fail(QC_ERR_STATE, "qc_set_local_state: qc_set_local_control has not been called");
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    QC_CUDA(cudaMemcpy2DAsync(pl->lc.p, qc::LC_STRIDE * sizeof(double), state, 4 * sizeof(double), 4 * sizeof(double),
+                              pl->d.batch, cudaMemcpyHostToDevice, pl->ctx->stream));
+    QC_CUDA(cudaStreamSynchronize(pl->ctx->stream));
     return QC_OK;
 }
 

@@ -28,6 +28,7 @@
 #include <cstdint>
 
 #include "qc_fft.cuh"
+#include "qc_local.cuh"
 
 namespace qc {
 
@@ -61,6 +62,11 @@ struct GridParams {
     const cd *traj_in;           // [batch][nt_max+1][N]  or null
     cd *traj_out;                // [batch][nt_max+1][N]  or null
     double *norms;               // [batch][2]
+    // field_mode 4 (local control with a fed-back carrier-frequency multiplier, qc_local.cuh)
+    double *lc;                  // [batch][LC_STRIDE] state and constants of the multiplier ODE
+    const double *lc_t;          // [batch][nt_max+1] step times t_l
+    const double *lc_rt;         // [nch][nch] transposed partial products of the Newton table
+    const double *lc_rdiag;      // [nch] reciprocal pivots
 };
 
 template <int LOG2N>
@@ -78,7 +84,7 @@ struct GridCfg {
     // shared memory (complex elements): per level transpose buffers A, B and the phi hand-over S ;
     // then dv, xp and 32 doubles of reduction scratch (the last one carries the TMEM base address)
     static constexpr size_t SMEM_BYTES =
-        sizeof(cd) * (size_t)(2 * (2 * BUF + N)) + sizeof(double) * (size_t)(3 * MAXCH + 32);
+        sizeof(cd) * (size_t)(2 * (2 * BUF + N)) + sizeof(double) * (size_t)(3 * MAXCH + 32 + LC_STRIDE + LS_COUNT);
 };
 
 // skewed position of element (k2, n3) inside a lane group's private 16*R3 region
@@ -172,7 +178,7 @@ __device__ __forceinline__ void level_sums(double val, double *s_red, int tid, d
     __syncthreads();
 }
 
-template <int LOG2N>
+template <int LOG2N, bool LOCAL = false>
 __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel(GridParams p) {
     typedef GridCfg<LOG2N> C;
     constexpr int N = C::N, TPL = C::TPL, R3 = C::R3, Q = C::Q, S1 = C::S1, BUF = C::BUF;
@@ -189,6 +195,8 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
     cd *s_dv = sm + 2 * (2 * BUF + N);
     double *s_xp = reinterpret_cast<double *>(s_dv + C::MAXCH);
     double *s_red = s_xp + C::MAXCH;              // 32 doubles of reduction scratch
+    double *s_lc = s_red + 32;                    // local control: the run's state / constants ...
+    double *s_ls = s_lc + LC_STRIDE;              // ... and the scalars of the current step
 
     const int run = p.run_first + blockIdx.x;
     if ((int)blockIdx.x >= p.run_count || run >= p.batch) return;
@@ -203,21 +211,21 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
         s_xp[i] = p.xp[i];
         s_dv[i] = p.dv[prun * p.nch + i];
     }
-    const double emin = p.sc[prun * 4 + 0], emax = p.sc[prun * 4 + 1], t_sc = p.sc[prun * 4 + 2],
-                 eL = p.sc[prun * 4 + 3];
-    const double c1 = 4.0 / (emax - emin);                       // phys_base.py:100
-    const double c2 = 2.0 * (emax + emin) / (emax - emin);       // phys_base.py:101
+    if (LOCAL && tid < LC_STRIDE) s_lc[tid] = p.lc[(long long)run * LC_STRIDE + tid];
+    double emin = p.sc[prun * 4 + 0], emax = p.sc[prun * 4 + 1], t_sc = p.sc[prun * 4 + 2], eL = p.sc[prun * 4 + 3];
+    double c1 = 4.0 / (emax - emin);                             // phys_base.py:100
+    double c2 = 2.0 * (emax + emin) / (emax - emin);             // phys_base.py:101
     const double dx = p.dx[(long long)p.dx_stride * run];
     const double h_lambda = p.ctl[(long long)p.ctl_stride * run * 4 + 0];
     const int nt = (int)p.ctl[(long long)p.ctl_stride * run * 4 + 1];
     double ph_s, ph_c;
     sincos(-2.0 * t_sc * (emax + emin) / (emax - emin), &ph_s, &ph_c);   // phys_base.py:174
-    const cd phase = cmk(ph_c, ph_s);
+    cd phase = cmk(ph_c, ph_s);
 
     // per-thread constants in registers: diagonal d(x) = c1*(v(x) +- eL) - c2 and the k-space multiplier
     // c1/N * akx2[k] at the (permuted) frequencies this thread holds after the forward transform
     double dcoef[16], kc[16];
-    {
+    auto load_coefs = [&]() {
         const double *vr = p.v + p.v_stride * run + (long long)lev * N;
         const double sgn = lev == 0 ? eL : -eL;                  // hamil_2d.py:50-51, 66-67
 #pragma unroll
@@ -229,7 +237,8 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
             const int k = k1p + 16 * (n3p * Q + q) + 256 * k3;
             kc[e] = p.kin[k] * kscale;
         }
-    }
+    };
+    load_coefs();
 
     cd psi[16], a[16];
     {
@@ -271,10 +280,23 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
 
     for (int l = p.l_first; l < p.l_first + p.nsteps && l <= nt; ++l) {
         const bool start_only = (l == 0);   // start(): only the initial field is evaluated (propagation.py:360-361)
+        // ---- local control: this step's multiplier, energy window and Newton table (qc_local.cuh) ----
+        if (LOCAL && !start_only) {
+            if (tid < 32)
+                local_step_setup(s_lc, s_ls, s_dv, s_xp, p.lc_rt, p.lc_rdiag, p.nch,
+                                 p.lc_t[(long long)run * (p.nt_max + 1) + l], l, tid);
+            __syncthreads();
+            if (s_ls[LS_STOP] != 0.0) break;             // the reference raises here (fitter.py:817-821)
+            eL = s_ls[LS_EL]; emin = s_ls[LS_EMIN]; emax = s_ls[LS_EMAX]; t_sc = s_ls[LS_TSC];
+            c1 = 4.0 / (emax - emin);
+            c2 = 2.0 * (emax + emin) / (emax - emin);
+            phase = cmk(s_ls[LS_PHR], s_ls[LS_PHI]);
+            load_coefs();
+        }
         // ---- rotating frame in (propagation.py:383-390) ---------------------
         cd eLx = cmk(1.0, 0.0);
         if (p.hf_hide && !start_only) {
-            eLx = p.expL[xrun + l];
+            eLx = LOCAL ? cmk(s_ls[LS_XR], s_ls[LS_XI]) : p.expL[xrun + l];
             const double den = eLx.x * eLx.x + eLx.y * eLx.y;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -292,7 +314,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
         if (p.single_step) {
             E = p.E_step[run].x;
             if (p.cplx_coupling) Ei = lev == 0 ? p.E_step[run].y : -p.E_step[run].y;
-        } else if (p.field_mode == 0) {
+        } else if (p.field_mode == 0 || LOCAL) {
             const int le = p.reversed_E ? (l == 0 ? nt : nt - l + 1) : l;
             E = p.E_base[erun + le].x;
         } else {
@@ -312,7 +334,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
             E = -2.0 * (tot * dx) / h_lambda;
         }
         if (tid == 0 && !p.single_step) {
-            E_out[l] = cmk(E, 0.0);
+            E_out[l] = cmk(E, LOCAL ? s_lc[LC_FM] : 0.0);      // local control: the multiplier rides in the imaginary slot
             if (p.write_E_base) p.E_base[erun + l] = cmk(E, 0.0);
         }
         if (start_only) continue;
@@ -460,6 +482,34 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
 #pragma unroll
                 for (int i = 0; i < 16; ++i) dst[t + TPL * i] = psi[i];
             }
+            // ---- local control: <psi_e|psi_g>, <psi_e|v_g - v_e|psi_g> and the feedback (propagation.py:435-437,
+            //      fitter.py:598-623); the two levels meet through the hand-over buffer -----------------------
+            if (LOCAL) {
+#pragma unroll
+                for (int n1 = 0; n1 < 16; ++n1) stash[t + TPL * n1] = psi[n1];
+                __syncthreads();
+                double q[4] = {0.0, 0.0, 0.0, 0.0};
+                if (lev == 0) {
+                    const double *v0 = p.v + p.v_stride * run, *v1 = v0 + N;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const cd u = stash_other[t + TPL * i];
+                        const double qr = psi[i].x * u.x + psi[i].y * u.y, qi = psi[i].x * u.y - psi[i].y * u.x;
+                        const double w = v0[t + TPL * i] - v1[t + TPL * i];
+                        q[0] += qr; q[1] += qi; q[2] += qr * w; q[3] += qi * w;
+                    }
+                }
+                double tot[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    double a0, a1;
+                    level_sums<C::NTHREADS, TPL>(q[c], s_red, tid, a0, a1);
+                    tot[c] = a0 + a1;
+                }
+                if (tid == 0) {
+                    local_feedback(s_lc, cmk(tot[0] * dx, tot[1] * dx), cmk(tot[2] * dx, tot[3] * dx));
+                }
+            }
             // ---- rotating frame out (propagation.py:440-441) ---------------------
             if (p.hf_hide) {
                 const double den = eLx.x * eLx.x + eLx.y * eLx.y;
@@ -481,6 +531,10 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
         cd *dst = p.psi + ((long long)run * 2 + lev) * N;
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) dst[t + TPL * n1] = psi[n1];
+    }
+    if (LOCAL) {
+        __syncthreads();
+        if (tid < LC_NSTATE) p.lc[(long long)run * LC_STRIDE + tid] = s_lc[tid];
     }
     tmem_wait_st();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

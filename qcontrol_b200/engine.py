@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import PlanDesc, SweepArgs, check, lib
 
 HAMIL_NONTRIV, HAMIL_TWO_LEVELS, HAMIL_BH_X, HAMIL_BH_Z, HAMIL_QUBIT = range(5)
-FIELD_PRESCRIBED, FIELD_KROTOV_FWD, FIELD_KROTOV_BWD, FIELD_UT_FWD = range(4)
+FIELD_PRESCRIBED, FIELD_KROTOV_FWD, FIELD_KROTOV_BWD, FIELD_UT_FWD, FIELD_LOCAL_PROJ = range(5)
 
 _DP = C.POINTER(C.c_double)
 
@@ -191,6 +191,28 @@ class Plan:
         assert psi_in.dtype == np.complex128 and psi_in.flags.c_contiguous and psi_in.shape == self.state_shape
         assert psi_out.dtype == np.complex128 and psi_out.flags.c_contiguous and psi_out.shape == self.state_shape
         check(lib.qc_propagate_host(self._h, C.byref(a), _ptr(psi_in.view(np.float64)), _ptr(psi_out.view(np.float64))))
+
+    def set_local_control(self, params, t_tab, xp):
+        """Constants of the fed-back multiplier ODE, params[batch][12] = extr(4), E0, nu_L, nu, k_E, lamb, pow,
+        epsilon, dt; step times t_tab[batch][nt_max+1]; nodes xp[nch].  Resets the feedback state."""
+        params = np.ascontiguousarray(params, np.float64)
+        t_tab = np.ascontiguousarray(t_tab, np.float64)
+        xp = np.ascontiguousarray(xp, np.float64)
+        assert params.shape == (self.batch, 12) and t_tab.shape == (self.batch, self.nt_max + 1) and xp.shape == (self.nch,)
+        check(lib.qc_set_local_control(self._h, _ptr(params), _ptr(t_tab), _ptr(xp)))
+
+    def get_local_state(self):
+        """[batch][11]: freq_mult, velocity, patched value, dAdt_happy, error code, psigc_psie, psigc_dv_psie,
+        dA/dt, error step."""
+        out = np.empty((self.batch, 11), np.float64)
+        check(lib.qc_get_local_state(self._h, _ptr(out)))
+        return out
+
+    def set_local_state(self, state):
+        """state[batch][4] = freq_mult, freq_mult_vel, freq_mult_patched, dAdt_happy (restart from a stored step)."""
+        state = np.ascontiguousarray(state, np.float64)
+        assert state.shape == (self.batch, 4)
+        check(lib.qc_set_local_state(self._h, _ptr(state)))
 
     def get_fields(self):
         out = np.empty((self.batch, self.nt_max + 1), np.complex128)

@@ -10,8 +10,9 @@ created (``create_propagation_reporter("iter_{k}f/basis_{v}", nlevs)``), they re
 ``print_iter_point_fitter`` receives the same rows (iter, goal_close, E_tlist, t_list, Fsm, E_int, J, nt).
 
 Supported task types: single_pot, filtering, trans_wo_control, intuitive_control,
-optimal_control_krotov, optimal_control_unit_transform.  The two local-control tasks feed every
-step's instrumentation back into the field (fitter.py:578-623) and are not ported yet.
+local_control_population, local_control_projection, optimal_control_krotov,
+optimal_control_unit_transform.  For local_control_projection the feedback of every step's overlaps
+into the carrier frequency (fitter.py:598-623, 814-836) runs inside the sweep kernel.
 """
 from __future__ import annotations
 
@@ -29,7 +30,8 @@ from .psi_basis import Psi, PsiBasis
 
 _TT = TaskRootConfiguration.TaskType
 _NAMES = {_TT.SINGLE_POT: "single_pot", _TT.FILTERING: "filtering", _TT.TRANS_WO_CONTROL: "trans_wo_control",
-          _TT.INTUITIVE_CONTROL: "intuitive_control", _TT.OPTIMAL_CONTROL_KROTOV: "optimal_control_krotov",
+          _TT.INTUITIVE_CONTROL: "intuitive_control", _TT.LOCAL_CONTROL_POPULATION: "local_control_population",
+          _TT.LOCAL_CONTROL_PROJECTION: "local_control_projection", _TT.OPTIMAL_CONTROL_KROTOV: "optimal_control_krotov",
           _TT.OPTIMAL_CONTROL_UNIT_TRANSFORM: "optimal_control_unit_transform"}
 _HAMIL = {_eng.HAMIL_NONTRIV: "ntriv", _eng.HAMIL_TWO_LEVELS: "two_levels", _eng.HAMIL_BH_X: "bh_x",
           _eng.HAMIL_BH_Z: "bh_z", _eng.HAMIL_QUBIT: "qubit"}
@@ -105,11 +107,24 @@ class FittingSolver:
             return "re"
         return "ss"
 
+    def _carrier(self):
+        """("exp", nu) when the high-frequency callable is exp(i 2 pi nu freq_mult t) (task_manager.py:73-86),
+        found by probing it; ("other", nu_L) otherwise.  Only the in-kernel multiplier feedback needs to know."""
+        import cmath
+        cf, cp = self.conf_fitter, self.conf_fitter.propagation
+        nu = getattr(getattr(self.laser_field_hf, "__self__", None), "nu", cp.nu_L)
+        fm, t = numpy.float64(1.25), numpy.float64(self.T) * 0.37
+        try:
+            got = complex(self.laser_field_hf(fm, t, cf.pcos, cf.w_list))
+        except Exception:
+            return "other", nu
+        want = cmath.exp(1j * 2.0 * math.pi * nu * fm * t)
+        return ("exp" if got == want else "other"), nu
+
     def _problem(self, dx, x, t_step, t_list):
         cf, cp = self.conf_fitter, self.conf_fitter.propagation
         if self.task_type not in _NAMES:
-            raise NotImplementedError("task type %s: the local-control feedback loops are not ported yet "
-                                      "(SURVEY.md 8f, row N2)" % self.task_type)
+            raise NotImplementedError("task type %s" % self.task_type)
         h = self.hamil2D
         mode = cf.h_lambda_mode
         return SimpleNamespace(
@@ -121,6 +136,7 @@ class FittingSolver:
             h_lambda=cf.h_lambda, h_lambda_mode=getattr(mode, "name", str(mode)).lower(), epsilon=cf.epsilon,
             iter_max=cf.iter_max, iter_mid_1=cf.iter_mid_1, iter_mid_2=cf.iter_mid_2, q=cf.q,
             impulses_number=cf.impulses_number, delay=cf.delay, F_type=self._functional_kind(), F_goal=self.Fgoal,
+            k_E=cf.k_E, lamb=cf.lamb, pow_=cf.pow, nu=self._carrier()[1], carrier=self._carrier()[0],
             t_step=t_step, t_list=t_list, laser_field=self.laser_field, laser_field_hf=self.laser_field_hf)
 
     # ------------------------------------------------------------------------------------------
@@ -139,9 +155,12 @@ class FittingSolver:
             self._open_id = prop_id
             batch.stride = min(report_stride(r) for r in self._reps)
         E = pl.get_fields()[0, l] if l > 0 else self._E0_of(prop_id, direction)
+        freq_mult = numpy.float64(1.0)
+        if pb.task_type == "local_control_projection" and l > 0:      # (E_l, freq_mult_l) share one slot
+            freq_mult, E = numpy.float64(numpy.imag(E)), numpy.float64(numpy.real(E))
         t = control.step_times(pb, direction)[l]
         if pb.hf_hide and l > 0:
-            exp_L = numpy.complex128(numpy.sqrt(complex(pb.laser_field_hf(numpy.float64(1.0), t, pb.pcos, pb.w_list))))
+            exp_L = numpy.complex128(numpy.sqrt(complex(pb.laser_field_hf(freq_mult, t, pb.pcos, pb.w_list))))
             E_full = E * exp_L * exp_L
         else:
             E_full = E if l > 0 else numpy.float64(0.0)
@@ -165,7 +184,7 @@ class FittingSolver:
             rep.print_time_point_prop(l, Psi.from_array(state[v]), t, pb.x, pb.np_, pb.nt, moms, smoms, ener,
                                       norms[v].astype(numpy.complex128), o0, of, [o0.sum(), of.sum()], ener.sum(),
                                       [tv[n, 16] for n in range(pb.nlevs)], [tv[n, 17] for n in range(pb.nlevs)], shown,
-                                      numpy.float64(1.0))
+                                      freq_mult)
 
     def _E0_of(self, prop_id, direction):
         """The field start() evaluates at l = 0 (propagation.py:360-361)."""
@@ -210,6 +229,12 @@ class FittingSolver:
                 if batch.errors[0]:
                     self._emit(hist[0], t_list, pb)
                     raise ValueError(batch.errors[0])
+            elif pb.task_type == "local_control_population":
+                hist = batch.run_local_population()
+            elif pb.task_type == "local_control_projection":
+                hist = batch.run_local_projection()
+                if batch.errors[0]:
+                    raise RuntimeError(batch.errors[0])
             else:
                 hist = batch.run_prescribed()
             self._emit(hist[0], t_list, pb)

@@ -28,7 +28,8 @@ from .config import TaskRootConfiguration
 
 _TT = TaskRootConfiguration.TaskType
 _NAMES = {_TT.SINGLE_POT: "single_pot", _TT.FILTERING: "filtering", _TT.TRANS_WO_CONTROL: "trans_wo_control",
-          _TT.INTUITIVE_CONTROL: "intuitive_control", _TT.OPTIMAL_CONTROL_KROTOV: "optimal_control_krotov",
+          _TT.INTUITIVE_CONTROL: "intuitive_control", _TT.LOCAL_CONTROL_POPULATION: "local_control_population",
+          _TT.LOCAL_CONTROL_PROJECTION: "local_control_projection", _TT.OPTIMAL_CONTROL_KROTOV: "optimal_control_krotov",
           _TT.OPTIMAL_CONTROL_UNIT_TRANSFORM: "optimal_control_unit_transform"}
 _HAMIL = {_eng.HAMIL_NONTRIV: "ntriv", _eng.HAMIL_TWO_LEVELS: "two_levels", _eng.HAMIL_BH_X: "bh_x",
           _eng.HAMIL_BH_Z: "bh_z", _eng.HAMIL_QUBIT: "qubit"}
@@ -92,7 +93,7 @@ def problem_from(conf, tm):
         nt=cp.nt, E0=cp.E0, t0=cp.t0, sigma=cp.sigma, nu_L=cp.nu_L, pcos=cf.pcos, w_list=cf.w_list,
         hf_hide=bool(cf.hf_hide), h_lambda=cf.h_lambda, h_lambda_mode=cf.h_lambda_mode.name.lower(), epsilon=cf.epsilon,
         iter_max=cf.iter_max, iter_mid_1=cf.iter_mid_1, iter_mid_2=cf.iter_mid_2, q=cf.q,
-        impulses_number=cf.impulses_number, delay=cf.delay,
+        impulses_number=cf.impulses_number, delay=cf.delay, k_E=cf.k_E, lamb=cf.lamb, pow_=cf.pow,
         F_type={F.FType.SM: "sm", F.FType.RE: "re", F.FType.SS: "ss"}[cf.F_type], F_goal=tm.F_goal, t_step=tm.t_step,
         t_list=tm.t_list, laser_field=tm.laser_field, laser_field_hf=tm.laser_field_hf,
         envelope=conf.init_guess.name.lower(), carrier=conf.init_guess_hf.name.lower(), nu=tm.nu)
@@ -147,6 +148,10 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True):
         elif tt == "optimal_control_unit_transform":
             tables_iter = str(data_rep.get("fitter", {}).get("plotting_flag", "")).lower() == "tables_iter"
             hist = b.run_unit_transform(keep_fields=not tables_iter)
+        elif tt == "local_control_population":
+            hist = b.run_local_population()
+        elif tt == "local_control_projection":
+            hist = b.run_local_projection()
         else:
             hist = b.run_prescribed()
         errors = getattr(b, "errors", [""] * len(idxs))

@@ -139,6 +139,18 @@ def conf_local(task, nt, k_E, lamb, pw, E0mult, np_=256, nt_pulse=None):
                                        "sigma": Tp / 6, "nu_L": 0.29297e15}}}
 
 
+def conf_local_shipped(task):
+    """The two local-control configurations of tests/functional_tests.py:508-544, 599-635 at full length."""
+    pop = task == "local_control_population"
+    return {"task_type": task, "pot_type": "morse", "wf_type": "morse", "hamil_type": "ntriv",
+            "init_guess": "gauss", "init_guess_hf": "exp", "nb": 1, "nlevs": 2, "T": 400e-15 if pop else 450e-15,
+            "L": 5.0, "np": 1024, "a": 1.0, "De": 20000.0, "x0p": -0.17, "a_e": 1.0, "De_e": 10000.0, "Du": 20000.0,
+            "fitter": {"k_E": 1e29, "lamb": 4e14 if pop else 8e14, "pow": 0.8 if pop else 0.65, "epsilon": 1e-15,
+                       "impulses_number": 1, "mod_log": 500,
+                       "propagation": {"m": 0.5, "nch": 64, "nt": 280000 if pop else 315000, "E0": 71.54,
+                                       "t0": 200e-15, "sigma": 50e-15, "nu_L": 0.29297e15}}}
+
+
 def conf_ut_jx(nt, iter_max, nlevs=2, w_list=(1.5, -1.0, 0.7999999999999998), T=5.4e-13):
     return {"task_type": "optimal_control_unit_transform", "pot_type": "none", "wf_type": "const",
             "hamil_type": "BH_model", "lf_aug_type": "x", "init_guess": "sqrsin", "init_guess_hf": "sin_set",
@@ -466,7 +478,8 @@ def case_shipped(R):
         out[fam + "__iter_E"] = np.array([r[2] for r in td.iter_tab_E], np.float64)
         out[fam + "__iter_t"] = np.array(td.iter_tab_E[0][1], np.float64)
     for fam in ("opt_ctrl_ut_HB_2lvls_Jx", "opt_ctrl_ut_HB_2lvls_Jz", "opt_ctrl_ut_HB_s2s_Jx", "pi_pulse",
-                "single_harm", "single_morse", "trans_woc", "opt_ctrl_krot", "filter", "int_ctrl"):
+                "single_harm", "single_morse", "trans_woc", "opt_ctrl_krot", "filter", "int_ctrl", "loc_ctrl_pop",
+                "loc_ctrl_proj"):
         td = load_table("fitter_" + fam)
         out[fam + "__tvals"] = np.array([[complex(c) for c in row] for row in td.tvals_tab], np.complex128)
     td = load_table("fit_iter_single_morse")

@@ -96,7 +96,8 @@ class _Rec:
                     self.rows.append(dict(l=l, t=t, psi=psi.as_array().copy(), momx=np.array(moms.x), momx2=np.array(moms.x2),
                                           momp=np.array(moms.p), momp2=np.array(moms.p2), ener=np.array(ener),
                                           norm=np.array(norm), overlp0=np.array(overlp0), overlpf=np.array(overlpf), E=E,
-                                          psi_max_abs=np.array(psi_max_abs), psi_max_real=np.array(psi_max_real)))
+                                          psi_max_abs=np.array(psi_max_abs), psi_max_real=np.array(psi_max_real),
+                                          freq_mult=freq_mult))
         p = P()
         self.props[prop_id] = p
         return p
