@@ -169,3 +169,65 @@ class TaskRootConfiguration(ConfigurationBase):
                      nb=1, nlevs=2, T=600e-15, L=5.0, np=1024, De=20000.0, De_e=10000.0, Du=20000.0, x0p=-0.17,
                      x0=0.0, p0=0.0, a=1.0, a_e=1.0, U=0.0, W=0.0, delta=1.0, t0_auto=False, nt_auto=False,
                      sigma_auto=False, nu_L_auto=False)
+
+
+class ReportRootConfiguration(ConfigurationBase):
+    """Report file of ``--json_rep`` (config.py:313-426 of the reference): one tree per output family, selected
+    by the key prefix ("table." / "plot."); un-prefixed keys (out_path, plotting_flag) are shared."""
+
+    class ReportFitterConfiguration(ConfigurationBase):
+        class OutputType(_NamedEnum):
+            ALL = 0
+            TABLES = 1
+            TABLES_ITER = 2
+            PLOTS = 3
+            NONE = 4
+
+        class ReportPropagationConfiguration(ConfigurationBase):
+            pass
+
+        class ReportTablePropagationConfiguration(ReportPropagationConfiguration):
+            def __init__(self, suffix=None):
+                super().__init__("table.")
+                self._define(tab_abs="tab_abs_{level}.csv", tab_real="tab_real_{level}.csv",
+                             tab_tvals="tab_tvals_{level}.csv", tab_tvals_fit="tab_tvals_fit.csv", lmin=0,
+                             mod_fileout=100)
+
+        class ReportPlotPropagationConfiguration(ReportPropagationConfiguration):
+            def __init__(self, suffix=None):
+                super().__init__("plot.")
+                self._define(lmin=0, mod_plotout=100, mod_update=20, number_plotout=15)
+
+        def __init__(self, key_prefix=""):
+            super().__init__(key_prefix)
+            R = ReportRootConfiguration.ReportFitterConfiguration
+            self._define(propagation=R.ReportPropagationConfiguration(key_prefix), out_path="output",
+                         table_glob_path="", plotting_flag=R.OutputType.ALL)
+
+    class ReportTableFitterConfiguration(ReportFitterConfiguration):
+        def __init__(self, suffix=None):
+            super().__init__("table.")
+            self._define(propagation=ReportRootConfiguration.ReportFitterConfiguration.ReportTablePropagationConfiguration(),
+                         tab_iter="tab_iter.csv", tab_iter_E="tab_iter_E.csv", imin=0, imod_fileout=1)
+
+    class ReportPlotFitterConfiguration(ReportFitterConfiguration):
+        def __init__(self, suffix=None):
+            super().__init__("plot.")
+            self._define(propagation=ReportRootConfiguration.ReportFitterConfiguration.ReportPlotPropagationConfiguration(),
+                         imin=0, imod_plotout=1, inumber_plotout=15)
+
+    def __init__(self, key_prefix=""):
+        super().__init__(key_prefix)
+        self._define(fitter=ReportRootConfiguration.ReportFitterConfiguration(key_prefix))
+
+
+class ReportTableRootConfiguration(ReportRootConfiguration):
+    def __init__(self):
+        super().__init__("table.")
+        self._define(fitter=ReportRootConfiguration.ReportTableFitterConfiguration())
+
+
+class ReportPlotRootConfiguration(ReportRootConfiguration):
+    def __init__(self):
+        super().__init__("plot.")
+        self._define(fitter=ReportRootConfiguration.ReportPlotFitterConfiguration())

@@ -57,6 +57,8 @@ def report_stride(rep) -> int:
     """How often a propagation reporter keeps a time point.  The reference calls reporters every step
     and lets them filter on ``l % mod == 0`` (reporter.py:110-164, tests/test_tools.py:189-194); reading
     that modulus lets the GPU path synchronise only on the steps that are actually recorded."""
+    if hasattr(rep, "reps"):          # MultiplePropagationReporter: the finest of its members, none = never
+        return min([report_stride(r) for r in rep.reps], default=1 << 30)
     for holder in (rep, getattr(rep, "conf", None), getattr(rep, "_conf", None)):
         if holder is None:
             continue
@@ -65,6 +67,97 @@ def report_stride(rep) -> int:
             if isinstance(v, int) and v > 0:
                 return v
     return 1
+
+
+class BatchObserver:
+    """The reporter side of a batched sweep: for every run of a ``control`` batch one FitterReporter; at step 0
+    and at every step the propagation reporters keep, the instrumentation of report_static / report_dynamic
+    (propagation.py:184-321) is evaluated on the device for the whole batch and each run's reporters receive
+    ``print_time_point_prop`` with the arguments the reference passes."""
+
+    def __init__(self, batch, reporters):
+        assert len(reporters) == batch.B
+        self.batch, self.reporters = batch, list(reporters)
+        self._open_id, self._reps = None, []
+
+    def close(self):
+        for per_run in self._reps:
+            for r in per_run:
+                r.close()
+        self._reps = []
+
+    def __call__(self, prop_id, l, direction, snaps):
+        batch = self.batch
+        pl = batch.plan
+        p0 = batch.pbs[0]
+        if prop_id != self._open_id:
+            self.close()
+            for rep, pb in zip(self.reporters, batch.pbs):
+                per_run = []
+                for v in range(pb.nb):
+                    r = rep.create_propagation_reporter(os.path.join(prop_id, "basis_" + str(v)), pb.nlevs)
+                    r.open()
+                    per_run.append(r)
+                self._reps.append(per_run)
+            self._open_id = prop_id
+            batch.stride = min(report_stride(r) for per_run in self._reps for r in per_run)
+        fields = pl.get_fields() if l > 0 else None
+        E_all, fm_all, Efull = [], [], numpy.zeros(batch.B, numpy.complex128)
+        for b, pb in enumerate(batch.pbs):
+            E = fields[b, min(l, pb.nt)] if l > 0 else self._E0_of(b, prop_id, direction)
+            freq_mult = numpy.float64(1.0)
+            if pb.task_type == "local_control_projection" and l > 0:      # (E_l, freq_mult_l) share one slot
+                freq_mult, E = numpy.float64(numpy.imag(E)), numpy.float64(numpy.real(E))
+            t = control.step_times(pb, direction)[min(l, pb.nt)]
+            if pb.hf_hide and l > 0:
+                exp_L = numpy.complex128(numpy.sqrt(complex(pb.laser_field_hf(freq_mult, t, pb.pcos, pb.w_list))))
+                Efull[b] = E * exp_L * exp_L
+            else:
+                Efull[b] = E if l > 0 else 0.0
+            E_all.append(E)
+            fm_all.append(freq_mult)
+        tab_all = pl.instrument(Efull, 2.0 * float(p0.m), snaps[0], snaps[1])       # [batch][nb][nlevs][20]
+        state_all = pl.get_state()
+        norms_all = pl.get_norms() if l > 0 else tab_all[:, :, :, 0]
+        for b, pb in enumerate(batch.pbs):
+            if l > pb.nt:                       # a shorter run of a ragged batch has already finished
+                continue
+            tab, state, norms, E = tab_all[b], state_all[b], norms_all[b], E_all[b]
+            t = control.step_times(pb, direction)[l]
+            shown = abs(E) if pb.ntriv == 1 else numpy.real(E)
+            for v, rep in enumerate(self._reps[b]):
+                tv = tab[v]
+                c = lambda a, b_: tv[:, a] + 1j * tv[:, b_]
+                moms = ExpectationValues(c(8, 9), c(10, 11), c(12, 13), c(14, 15))
+                if pb.ntriv != 1:
+                    moms.p = numpy.zeros(pb.nlevs, numpy.complex128)
+                    moms.p2 = numpy.zeros(pb.nlevs, numpy.complex128)
+                if pb.ntriv != 1 and pb.nlevs == 2:
+                    cross = tv[0, 18] + 1j * tv[0, 19]
+                    smoms = SigmaExpectationValues(2.0 * cross.real, 2.0 * cross.imag, complex(tv[0, 0] - tv[1, 0]))
+                else:
+                    smoms = SigmaExpectationValues(numpy.float64(0.0), numpy.float64(0.0), numpy.float64(0.0))
+                ener, o0, of = c(2, 3), c(4, 5), c(6, 7)
+                rep.print_time_point_prop(l, Psi.from_array(state[v]), t, pb.x, pb.np_, pb.nt, moms, smoms, ener,
+                                          norms[v].astype(numpy.complex128), o0, of, [o0.sum(), of.sum()], ener.sum(),
+                                          [tv[n, 16] for n in range(pb.nlevs)], [tv[n, 17] for n in range(pb.nlevs)], shown,
+                                          fm_all[b])
+
+    def _E0_of(self, b, prop_id, direction):
+        """The field start() evaluates at l = 0 (propagation.py:360-361)."""
+        pb = self.batch.pbs[b]
+        it = int(prop_id.split("_")[1][:-1])
+        if direction == control.BACKWARD:
+            if pb.task_type == "optimal_control_unit_transform" and it > 0:
+                return self.batch.plan.get_fields()[b, pb.nt]
+            if pb.task_type == "optimal_control_krotov":
+                return numpy.float64(0.0)
+            return pb.laser_field(pb.E0, pb.T, pb.t0, pb.sigma) * (
+                1.0 if pb.ntriv == 1 else pb.laser_field_hf(numpy.float64(1.0), pb.T, pb.pcos, pb.w_list))
+        if pb.task_type == "optimal_control_krotov" and it > 0:
+            return self.batch.plan.get_fields()[b, 0]
+        env = pb.laser_field(pb.E0, numpy.float64(0.0), pb.t0, pb.sigma)
+        return env if pb.hf_hide else env * pb.laser_field_hf(numpy.float64(1.0), numpy.float64(0.0), pb.pcos, pb.w_list)
 
 
 class FittingSolver:
@@ -140,72 +233,9 @@ class FittingSolver:
             t_step=t_step, t_list=t_list, laser_field=self.laser_field, laser_field_hf=self.laser_field_hf)
 
     # ------------------------------------------------------------------------------------------
-    def _observe(self, prop_id, l, direction, snaps):
-        """Instrumentation of the resident state on the device and the reporter call of report_static /
-        report_dynamic (propagation.py:184-321) for every basis vector."""
-        batch, pb = self._batch, self._pb
-        pl = batch.plan
-        if prop_id != self._open_id:
-            self._close_reporters()
-            self._reps = []
-            for v in range(pb.nb):
-                r = self.reporter.create_propagation_reporter(os.path.join(prop_id, "basis_" + str(v)), pb.nlevs)
-                r.open()
-                self._reps.append(r)
-            self._open_id = prop_id
-            batch.stride = min(report_stride(r) for r in self._reps)
-        E = pl.get_fields()[0, l] if l > 0 else self._E0_of(prop_id, direction)
-        freq_mult = numpy.float64(1.0)
-        if pb.task_type == "local_control_projection" and l > 0:      # (E_l, freq_mult_l) share one slot
-            freq_mult, E = numpy.float64(numpy.imag(E)), numpy.float64(numpy.real(E))
-        t = control.step_times(pb, direction)[l]
-        if pb.hf_hide and l > 0:
-            exp_L = numpy.complex128(numpy.sqrt(complex(pb.laser_field_hf(freq_mult, t, pb.pcos, pb.w_list))))
-            E_full = E * exp_L * exp_L
-        else:
-            E_full = E if l > 0 else numpy.float64(0.0)
-        tab = pl.instrument(E_full, 2.0 * float(pb.m), snaps[0], snaps[1])[0]       # [nb][nlevs][20]
-        state = pl.get_state()[0]
-        norms = pl.get_norms()[0] if l > 0 else tab[:, :, 0]
-        shown = abs(E) if pb.ntriv == 1 else numpy.real(E)
-        for v, rep in enumerate(self._reps):
-            tv = tab[v]
-            c = lambda a, b: tv[:, a] + 1j * tv[:, b]
-            moms = ExpectationValues(c(8, 9), c(10, 11), c(12, 13), c(14, 15))
-            if pb.ntriv != 1:
-                moms.p = numpy.zeros(pb.nlevs, numpy.complex128)
-                moms.p2 = numpy.zeros(pb.nlevs, numpy.complex128)
-            if pb.ntriv != 1 and pb.nlevs == 2:
-                cross = tv[0, 18] + 1j * tv[0, 19]
-                smoms = SigmaExpectationValues(2.0 * cross.real, 2.0 * cross.imag, complex(tv[0, 0] - tv[1, 0]))
-            else:
-                smoms = SigmaExpectationValues(numpy.float64(0.0), numpy.float64(0.0), numpy.float64(0.0))
-            ener, o0, of = c(2, 3), c(4, 5), c(6, 7)
-            rep.print_time_point_prop(l, Psi.from_array(state[v]), t, pb.x, pb.np_, pb.nt, moms, smoms, ener,
-                                      norms[v].astype(numpy.complex128), o0, of, [o0.sum(), of.sum()], ener.sum(),
-                                      [tv[n, 16] for n in range(pb.nlevs)], [tv[n, 17] for n in range(pb.nlevs)], shown,
-                                      freq_mult)
-
-    def _E0_of(self, prop_id, direction):
-        """The field start() evaluates at l = 0 (propagation.py:360-361)."""
-        pb = self._pb
-        it = int(prop_id.split("_")[1][:-1])
-        if direction == control.BACKWARD:
-            if pb.task_type == "optimal_control_unit_transform" and it > 0:
-                return self._batch.plan.get_fields()[0, pb.nt]
-            if pb.task_type == "optimal_control_krotov":
-                return numpy.float64(0.0)
-            return pb.laser_field(pb.E0, pb.T, pb.t0, pb.sigma) * (
-                1.0 if pb.ntriv == 1 else pb.laser_field_hf(numpy.float64(1.0), pb.T, pb.pcos, pb.w_list))
-        if pb.task_type == "optimal_control_krotov" and it > 0:
-            return self._batch.plan.get_fields()[0, 0]
-        env = pb.laser_field(pb.E0, numpy.float64(0.0), pb.t0, pb.sigma)
-        return env if pb.hf_hide else env * pb.laser_field_hf(numpy.float64(1.0), numpy.float64(0.0), pb.pcos, pb.w_list)
-
     def _close_reporters(self):
-        for r in getattr(self, "_reps", []):
-            r.close()
-        self._reps = []
+        if getattr(self, "_observer", None) is not None:
+            self._observer.close()
 
     # ------------------------------------------------------------------------------------------
     def time_propagation(self, dx, x, t_step, t_list):
@@ -219,8 +249,7 @@ class FittingSolver:
             akx = numpy.ascontiguousarray((math_base.initak(pb.np_, dx, 1, pb.ntriv) *
                                            (phys_base.hart_to_cm / (-1j) / phys_base.dalt_to_au)).real)
         batch.plan.set_instr_grid(numpy.asarray(x, numpy.float64), akx)
-        self._open_id, self._reps = None, []
-        batch.observer = self._observe
+        self._observer = batch.observer = BatchObserver(batch, [self.reporter])
         try:
             if pb.task_type == "optimal_control_krotov":
                 hist = batch.run_krotov()

@@ -6,9 +6,10 @@
 The task template is expanded over its "@SUBST:LIST" entries exactly like the reference does; instead of
 one thread-pool job (or SLURM job) per variant, variants that share a plan shape become ONE batched plan
 per GPU, the variants are split over the ranks by longest-processing-time-first, and each rank writes the
-iteration tables of its own runs (tab_iter.csv / tab_iter_E.csv, reporter.py:609-632) under the report's
-``out_path`` (with the reference's ``{input:$.json.path}`` templating).  Per-step tables and plots are the
-reference's I/O layer and are not reproduced here.
+output of its own runs under the report's ``out_path`` (with the reference's ``{input:$.json.path}``
+templating) through ``qcontrol_b200.reporter``: ``table_inp_-1.txt`` (newcheb.py:526-573), tab_iter.csv /
+tab_iter_E.csv, and -- for plotting_flag "tables" / "all" -- the per-step tables of every sweep
+(reporter.py:73-164).  The HTML plots are presentation only and are not reproduced.
 """
 from __future__ import annotations
 
@@ -23,8 +24,8 @@ from types import SimpleNamespace
 import numpy
 
 from . import batch as qbatch
-from . import control, engine as _eng, task_manager
-from .config import TaskRootConfiguration
+from . import control, engine as _eng, math_base, phys_base, reporter, task_manager
+from .config import ReportPlotRootConfiguration, ReportRootConfiguration, ReportTableRootConfiguration, TaskRootConfiguration
 
 _TT = TaskRootConfiguration.TaskType
 _NAMES = {_TT.SINGLE_POT: "single_pot", _TT.FILTERING: "filtering", _TT.TRANS_WO_CONTROL: "trans_wo_control",
@@ -99,6 +100,28 @@ def problem_from(conf, tm):
         envelope=conf.init_guess.name.lower(), carrier=conf.init_guess_hf.name.lower(), nu=tm.nu)
 
 
+def print_input(out_path, conf_task, file_name):
+    """The parameter sheet post_processing.py reads (newcheb.py:526-573): same keys, tabs and number formats."""
+    c, f, p = conf_task, conf_task.fitter, conf_task.fitter.propagation
+    rows = [("task_type:\t\t", c.task_type), ("iter_max:\t\t", f.iter_max), ("iter_mid_1:\t\t", f.iter_mid_1),
+            ("iter_mid_2:\t\t", f.iter_mid_2), ("q:\t\t\t", f.q), ("epsilon:\t\t", "%.1E" % f.epsilon),
+            ("nb:\t\t\t", c.nb), ("nlevs:\t\t\t", c.nlevs), ("wf_type:\t\t", c.wf_type),
+            ("impulses_number:\t", f.impulses_number), ("Em:\t\t\t", f.Em), ("E0:\t\t\t", p.E0), ("t0:\t\t\t", p.t0),
+            ("t0_auto:\t\t", c.t0_auto), ("sigma:\t\t\t", "%.6E" % p.sigma), ("sigma_auto:\t\t", c.sigma_auto),
+            ("nu_L:\t\t\t", "%.6E" % p.nu_L), ("nu_L_auto:\t\t", c.nu_L_auto), ("h_lambda:\t\t", f.h_lambda),
+            ("h_lambda_mode:\t\t", f.h_lambda_mode), ("init_guess:\t\t", c.init_guess),
+            ("init_guess_hf:\t\t", c.init_guess_hf), ("F_type:\t\t\t", f.F_type), ("pcos:\t\t\t", f.pcos),
+            ("hf_hide:\t\t", f.hf_hide), ("w_list:\t\t\t", f.w_list), ("w_min:\t\t\t", f.w_min), ("w_max:\t\t\t", f.w_max),
+            ("hamil_type:\t\t", c.hamil_type), ("U:\t\t\t", c.U), ("W:\t\t\t", c.W), ("delta:\t\t\t", c.delta),
+            ("lf_aug_type:\t\t", c.lf_aug_type), ("pot_type:\t\t", c.pot_type), ("Du:\t\t\t", c.Du), ("np:\t\t\t", c.np),
+            ("L:\t\t\t", c.L), ("nch:\t\t\t", p.nch), ("nt:\t\t\t", p.nt), ("nt_auto:\t\t", c.nt_auto),
+            ("T:\t\t\t", "%.6E" % c.T)]
+    os.makedirs(out_path, exist_ok=True)
+    with open(os.path.join(out_path, file_name), "w") as finp:
+        for label, val in rows:
+            finp.write("%s%s\n" % (label, val))
+
+
 def write_tables(out_path, rows, t_list, nt, imin=-1):
     """tab_iter.csv / tab_iter_E.csv in the reference's format (reporter.py:609-632)."""
     os.makedirs(out_path, exist_ok=True)
@@ -134,14 +157,30 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True):
     mine = qbatch.lpt_shards(costs, world)[rank]
     results = {}
     ctx = _eng.Context(local)
+    OT = ReportRootConfiguration.ReportFitterConfiguration.OutputType
     for shape, idxs in qbatch.plan_groups(shapes, mine).items():
-        pbs = []
+        pbs, reps = [], []
         for i in idxs:
             with contextlib.redirect_stdout(io.StringIO()):
                 tm = task_manager.create(confs[i])
+                rep_json = resolve_input_templates(variants[i], copy.deepcopy(data_rep))
+                ct, cp = ReportTableRootConfiguration(), ReportPlotRootConfiguration()
+                ct.load(rep_json)
+                cp.load(rep_json)
+            print_input(ct.fitter.out_path, confs[i], "table_inp_-1.txt")
+            reps.append(reporter.MultipleFitterReporter(ct.fitter, cp.fitter).open())
             pbs.append(problem_from(confs[i], tm))
         grid = pbs[0].hamil == "ntriv"
         b = (control.GridBatch if grid else control.NLevelBatch)(pbs, ctx=ctx)
+        if any(r.conf_rep_table.plotting_flag in (OT.ALL, OT.TABLES) for r in reps):
+            # per-step tables were asked for: instrument the resident states at the steps the tables keep
+            from .fitter import BatchObserver
+            akx = None
+            if grid:
+                akx = numpy.ascontiguousarray((math_base.initak(pbs[0].np_, pbs[0].dx, 1, pbs[0].ntriv) *
+                                               (phys_base.hart_to_cm / (-1j) / phys_base.dalt_to_au)).real)
+            b.plan.set_instr_grid(numpy.asarray(pbs[0].x, numpy.float64), akx)
+            b.observer = BatchObserver(b, reps)
         tt = pbs[0].task_type
         if tt == "optimal_control_krotov":
             hist = b.run_krotov()
@@ -155,11 +194,15 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True):
         else:
             hist = b.run_prescribed()
         errors = getattr(b, "errors", [""] * len(idxs))
+        if b.observer is not None:
+            b.observer.close()
         for k, i in enumerate(idxs):
             results[i] = hist[k]
-            rep = resolve_input_templates(variants[i], copy.deepcopy(data_rep))
-            out_path = rep.get("fitter", {}).get("out_path", "output")
-            write_tables(out_path, hist[k], pbs[k].t_list, pbs[k].nt, rep.get("fitter", {}).get("table.imin", -1))
+            for r in hist[k]:
+                reps[k].print_iter_point_fitter(r.it, r.goal_close, None if r.E_tlist is None else list(r.E_tlist),
+                                                pbs[k].t_list, numpy.complex128(r.Fsm), numpy.float64(r.E_int), r.J,
+                                                pbs[k].nt)
+            reps[k].close()
             if errors[k] and verbose:
                 print("An exception interrupted the job #%d: %s" % (i, errors[k]), file=sys.stderr)
             elif verbose:

@@ -468,6 +468,73 @@ def case_fitter_nlevel(R):
         save(name, **out)
 
 
+def report_inputs():
+    """Deterministic inputs for the table reporters: three time points of a 2-level, 8-point state and three
+    iteration rows.  Shared by the generator (reference reporters) and tests/test_host.py (our reporters)."""
+    rng = np.random.default_rng(2024)
+    x = np.linspace(-1.5, 2.0, 8)
+    pts = []
+    for l in (0, 2, 3, 4):
+        c = lambda n=2: rng.normal(size=n) + 1j * rng.normal(size=n)
+        pts.append(dict(l=l, psi=rng.normal(size=(2, 8)) + 1j * rng.normal(size=(2, 8)), t=l * 1.25e-15, momx=c(), momx2=c(),
+                        momp=c(), momp2=c(), smoms=c(3), ener=c() * 1e3, norm=c(), overlp0=c(), overlpf=c(),
+                        overlp_tot=c(), ener_tot=complex(c(1)[0]) * 1e3, psi_max_abs=rng.random(2), psi_max_real=rng.normal(size=2),
+                        E=complex(c(1)[0]) * 40 if l != 2 else np.float64(-12.5), freq_mult=np.float64(1.0 + 0.1 * l)))
+    iters = [(-1, 0.25, np.complex128(-0.0625), np.float64(1234.56789), -0.07, rng.normal(size=5), [k * 1e-15 for k in range(5)]),
+             (0, 0.5, np.complex128(-0.25 + 0.1j), np.float64(2234.5), -0.3, rng.normal(size=5) + 1j * rng.normal(size=5),
+              [k * 1e-15 for k in range(5)]),
+             (1, 0.75, np.complex128(-0.5625), np.float64(3234.5), -0.6, rng.normal(size=5), [k * 1e-15 for k in range(5)])]
+    return x, pts, iters
+
+
+def case_report_tables(R):
+    """File contents written by the reference's table reporters (reporter.py:73-164, 581-632, 790-834) for the
+    inputs of ``report_inputs`` under plotting_flag "tables" and "tables_iter"."""
+    import tempfile
+    x, pts, iters = report_inputs()
+    out = {}
+    for flag in ("tables", "tables_iter"):
+        with tempfile.TemporaryDirectory() as tmp, quiet():
+            rep_json = {"fitter": {"out_path": os.path.join(tmp, "out"), "plotting_flag": flag, "table.imin": -1,
+                                   "table.imod_fileout": 1, "table.tab_iter": "tab_iter.csv",
+                                   "table.tab_iter_E": "tab_iter_E.csv", "plot.imin": -1,
+                                   "propagation": {"table.lmin": 2, "table.mod_fileout": 2,
+                                                   "table.tab_abs": "tab_abs_{level}.csv",
+                                                   "table.tab_real": "tab_real_{level}.csv",
+                                                   "table.tab_tvals": "tab_tvals_{level}.csv",
+                                                   "table.tab_tvals_fit": "tab_tvals_fit.csv", "plot.lmin": 0}}}
+            ct = R.config.ReportTableRootConfiguration()
+            ct.load(rep_json)
+            cp = R.config.ReportPlotRootConfiguration()
+            cp.load(rep_json)
+            fr = R.reporter.MultipleFitterReporter(conf_rep_table=ct.fitter, conf_rep_plot=cp.fitter)
+            fr.open()
+            pr = fr.create_propagation_reporter(os.path.join("iter_0f", "basis_0"), 2)
+            pr.open()
+            for p in pts:
+                psi = R.psi_basis.Psi(f=[p["psi"][0].copy(), p["psi"][1].copy()])
+                moms = R.phys_base.ExpectationValues(p["momx"], p["momx2"], p["momp"], p["momp2"])
+                sm = R.phys_base.SigmaExpectationValues(p["smoms"][0], p["smoms"][1], p["smoms"][2])
+                pr.print_time_point_prop(p["l"], psi, p["t"], x, 8, 4, moms, sm, p["ener"], p["norm"], p["overlp0"],
+                                         p["overlpf"], p["overlp_tot"], p["ener_tot"], p["psi_max_abs"], p["psi_max_real"],
+                                         p["E"], p["freq_mult"])
+            for r in pr.reps:
+                r.close()
+            for it, gc, F, Ei, J, El, tl in iters:
+                fr.print_iter_point_fitter(it, gc, list(El), tl, F, Ei, J, 4)
+            for r in fr.reps:
+                try:
+                    r.close()
+                except AttributeError:      # TableFitterReporter.close() trips over f_ifit_E = None for tables_iter
+                    pass
+            for root, _, files in os.walk(os.path.join(tmp, "out")):
+                for fn in files:
+                    rel = os.path.relpath(os.path.join(root, fn), os.path.join(tmp, "out"))
+                    with open(os.path.join(root, fn)) as f:
+                        out[flag + "::" + rel.replace(os.sep, "/")] = np.array(f.read())
+    save("report_tables", **out)
+
+
 def case_shipped(R):
     """Rows of the reference's shipped golden tables (test_data/*.py), stored as
     arrays so they can be checked on the GPU box."""
@@ -504,7 +571,7 @@ def case_shipped(R):
 
 
 CASES = {"kat": case_kat, "one_step": case_one_step, "fitter_grid": case_fitter_grid,
-         "fitter_nlevel": case_fitter_nlevel, "fitter_local": case_fitter_local, "shipped": case_shipped}
+         "fitter_nlevel": case_fitter_nlevel, "fitter_local": case_fitter_local, "report_tables": case_report_tables, "shipped": case_shipped}
 
 if __name__ == "__main__":
     R = load_reference()

@@ -196,7 +196,8 @@ def test_batch_entry_point(tmp_path):
     tpl["nt_auto"] = True
     tpl["fitter"]["w_list"] = []
     tpl["fitter"]["h_lambda"] = 5e-4          # well-conditioned (see DESIGN.md "Conditioning")
-    rep = {"fitter": {"out_path": str(tmp_path / "out_{input:$.run_id}" / "T={input:$.T}"), "table.imin": -1}}
+    rep = {"fitter": {"out_path": str(tmp_path / "out_{input:$.run_id}" / "T={input:$.T}"), "table.imin": -1,
+                      "propagation": {"table.mod_fileout": 100}}}
     variants = batch.expand_substitutions(tpl)
     assert len(variants) == 4
     res = newcheb.run_variants(variants, rep, seed_base=1000, device=0, verbose=False)
@@ -214,3 +215,11 @@ def test_batch_entry_point(tmp_path):
         assert lines[1].split()[0] == "0" and abs(float(lines[1].split()[2]) - tab[1, 2]) < 1e-6
         nE = (tmp_path / ("out_%s" % var["run_id"]) / ("T=%s" % var["T"]) / "tab_iter_E.csv").read_text().count("\n")
         assert nE == len(rows) * (pb.nt + 1)
+        # the parameter sheet post_processing.py parses, and the per-step tables of a sweep (plotting_flag default = all)
+        sheet = (path.parent / "table_inp_-1.txt").read_text()
+        assert "nb:\t\t\t2\n" in sheet and "iter_mid_2:\t\t300\n" in sheet and "epsilon:\t\t" in sheet
+        fit_tab = (path.parent / "iter_1f" / "basis_1" / "tables" / "tab_tvals_fit.csv").read_text().strip().splitlines()
+        assert len(fit_tab) == pb.nt // 100 + 1
+        assert abs(float(fit_tab[1].split()[0]) - 100 * pb.t_step * 1e15) < 1e-6
+        abs0 = (path.parent / "iter_0b" / "basis_0" / "tables" / "tab_abs_0.csv").read_text().strip().splitlines()
+        assert len(abs0) == pb.nt // 100 + 1

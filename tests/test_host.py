@@ -143,3 +143,51 @@ def test_lpt_sharding_is_balanced_and_deterministic():
     assert max(loads) / min(loads) < 1.01
     assert shards == batch.lpt_shards(nts, 8)
     assert batch.lpt_shards([3.0], 4) == [[0], [], [], []]
+
+
+@pytest.mark.parametrize("flag", ["tables", "tables_iter"])
+def test_table_reporters_write_the_reference_formats(golden, tmp_path, flag):
+    """tab_iter / tab_iter_E / tab_abs / tab_real / tab_tvals / tab_tvals_fit files, byte for byte
+    what the reference's reporters (reporter.py:73-164, 581-632, 790-834) write for the same inputs."""
+    import os
+    from qcontrol_b200 import config, reporter
+    from qcontrol_b200.phys_base import ExpectationValues, SigmaExpectationValues
+    from qcontrol_b200.psi_basis import Psi
+    import tests.golden.gen_golden as gg
+    g = golden("report_tables")
+    x, pts, iters = gg.report_inputs()
+    out = str(tmp_path / "out")
+    rep_json = {"fitter": {"out_path": out, "plotting_flag": flag, "table.imin": -1, "table.imod_fileout": 1,
+                           "table.tab_iter": "tab_iter.csv", "table.tab_iter_E": "tab_iter_E.csv", "plot.imin": -1,
+                           "propagation": {"table.lmin": 2, "table.mod_fileout": 2, "table.tab_abs": "tab_abs_{level}.csv",
+                                           "table.tab_real": "tab_real_{level}.csv", "table.tab_tvals": "tab_tvals_{level}.csv",
+                                           "table.tab_tvals_fit": "tab_tvals_fit.csv", "plot.lmin": 0}}}
+    with contextlib.redirect_stdout(io.StringIO()):
+        ct = config.ReportTableRootConfiguration()
+        ct.load(rep_json)
+        cp = config.ReportPlotRootConfiguration()
+        cp.load(rep_json)
+    assert ct.fitter.propagation.mod_fileout == 2 and ct.fitter.imin == -1 and cp.fitter.imin == -1
+    fr = reporter.MultipleFitterReporter(conf_rep_table=ct.fitter, conf_rep_plot=cp.fitter)
+    fr.open()
+    pr = fr.create_propagation_reporter(os.path.join("iter_0f", "basis_0"), 2)
+    pr.open()
+    for p in pts:
+        pr.print_time_point_prop(p["l"], Psi.from_array(p["psi"]), p["t"], x, 8, 4,
+                                 ExpectationValues(p["momx"], p["momx2"], p["momp"], p["momp2"]),
+                                 SigmaExpectationValues(p["smoms"][0], p["smoms"][1], p["smoms"][2]), p["ener"], p["norm"],
+                                 p["overlp0"], p["overlpf"], p["overlp_tot"], p["ener_tot"], p["psi_max_abs"],
+                                 p["psi_max_real"], p["E"], p["freq_mult"])
+    pr.close()
+    for it, gc, F, Ei, J, El, tl in iters:
+        fr.print_iter_point_fitter(it, gc, list(El), tl, F, Ei, J, 4)
+    fr.close()
+    want = {k.split("::", 1)[1]: str(g[k]) for k in g if k.startswith(flag + "::")}
+    got = {}
+    for root, _, files in os.walk(out):
+        for fn in files:
+            with open(os.path.join(root, fn)) as f:
+                got[os.path.relpath(os.path.join(root, fn), out).replace(os.sep, "/")] = f.read()
+    assert sorted(got) == sorted(want)
+    for k in want:
+        assert got[k] == want[k], k
