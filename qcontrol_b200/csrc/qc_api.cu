@@ -706,7 +706,12 @@ template <int NL>
 static int32_t launch_nlevel(qc_plan *pl, const qc::NLevelParams &np_) {
     const int threads = 128;
     const unsigned blocks = (unsigned)((np_.nthreads + threads - 1) / threads);
-    qc::nlevel_sweep_kernel<NL><<<blocks, threads, 0, pl->ctx->stream>>>(np_);
+    if (np_.nch <= 8)
+        qc::nlevel_sweep_kernel<NL, 8><<<blocks, threads, 0, pl->ctx->stream>>>(np_);
+    else if (np_.nch <= 16)
+        qc::nlevel_sweep_kernel<NL, 16><<<blocks, threads, 0, pl->ctx->stream>>>(np_);
+    else
+        qc::nlevel_sweep_kernel<NL, 0><<<blocks, threads, 0, pl->ctx->stream>>>(np_);
     pl->ctx->launches++;
     QC_CUDA(cudaGetLastError());
     return QC_OK;

@@ -56,7 +56,10 @@ __device__ __forceinline__ void tri_apply(const double *dg, const cd *up, const 
     }
 }
 
-template <int NL>
+// NCH > 0: the interpolation nodes and coefficients (nch <= NCH) are cached in registers and the polynomial loop
+// is unrolled, so the time loop has no loads besides the one-step-ahead prefetch; NCH == 0: any nch, read
+// through L1 every order.
+template <int NL, int NCH>
 __global__ void __launch_bounds__(128) nlevel_sweep_kernel(NLevelParams p) {
     const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_range = gt < p.nthreads;
@@ -78,6 +81,16 @@ __global__ void __launch_bounds__(128) nlevel_sweep_kernel(NLevelParams p) {
     sincos(-2.0 * t_sc * (emax + emin) / (emax - emin), &ph_s, &ph_c);
     const cd phase = cmk(ph_c, ph_s);
     const cd *dv = p.dv + prun * p.nch;
+    constexpr int NCR = NCH > 0 ? NCH : 1;
+    double xp_r[NCR];
+    cd dv_r[NCR];
+    if (NCH > 0) {
+#pragma unroll
+        for (int j = 0; j < NCR; ++j) {
+            xp_r[j] = j < p.nch ? p.xp[j] : 0.0;
+            dv_r[j] = j < p.nch ? dv[j] : cmk(0.0, 0.0);
+        }
+    }
     const cd a0 = (p.a0 && active) ? p.a0[(long long)run * p.nb + vec] : cmk(0.0, 0.0);
 
     // E-independent parts of the level matrix
@@ -107,25 +120,55 @@ __global__ void __launch_bounds__(128) nlevel_sweep_kernel(NLevelParams p) {
     cd *E_out = p.E_out + (long long)run * (p.nt_max + 1);
     const long long slice = (long long)NL * p.nthreads;
 
+    // The per-step inputs (field table entry, envelope, the stored slice of the opposite sweep) depend only on
+    // the step number: they are fetched one step ahead, so their HBM latency (every slice is touched once) is
+    // hidden behind the polynomial recurrence of the current step instead of heading its dependency chain.
+    struct StepIn {
+        cd base, chi[NL];
+        double s;
+    };
+    const bool ut = !p.single_step && p.field_mode != 0;
+    auto fetch = [&](int l) {
+        StepIn in;
+        in.base = cmk(0.0, 0.0);
+        in.s = 0.0;
+#pragma unroll
+        for (int n = 0; n < NL; ++n) in.chi[n] = cmk(0.0, 0.0);
+        if (p.single_step || l > nt || l >= p.l_first + p.nsteps) return in;
+        if (!ut) {
+            const int le = p.reversed_E ? (l == 0 ? nt : nt - l + 1) : l;
+            in.base = p.E_base[erun + le];
+            return in;
+        }
+        in.base = p.E_base[erun + l];
+        in.s = p.s_env[srun + l].x;
+        if (active && l > 0) {
+            // UT forward (fitter.py:739-778): chi_tlist[-l] is slice nt+1-l of the backward record
+            const cd *tr = p.traj_in + (long long)(nt + 1 - l) * slice + gt;
+#pragma unroll
+            for (int n = 0; n < NL; ++n) in.chi[n] = tr[(long long)n * p.nthreads];
+        }
+        return in;
+    };
+    StepIn nxt = fetch(p.l_first);
+    const cd E_single = p.single_step ? p.E_step[run] : cmk(0.0, 0.0);
+
     for (int l = p.l_first; l < p.l_first + p.nsteps; ++l) {
         const bool live = active && l <= nt;
+        const StepIn cur = nxt;
         // ---- field -------------------------------------------------------------
         cd E;
         if (p.single_step) {
-            E = p.E_step[run];
-        } else if (p.field_mode == 0) {
-            const int le = p.reversed_E ? (l == 0 ? nt : nt - l + 1) : l;
-            E = (l <= nt) ? p.E_base[erun + le] : cmk(0.0, 0.0);
+            E = E_single;
+        } else if (!ut) {
+            E = cur.base;
         } else {
-            // UT forward (fitter.py:739-778): chi_tlist[-l] is slice nt+1-l of the backward record
             cd part = cmk(0.0, 0.0);
             if (live && l > 0) {
-                const cd *tr = p.traj_in + (long long)(nt + 1 - l) * slice + gt;
 #pragma unroll
                 for (int n = 0; n < NL; ++n) {
-                    const cd c = tr[(long long)n * p.nthreads];
                     // a0[v] * cprod(chi, psi),  cprod(chi, psi) = dx * conj(psi) * chi  (math_base.py:21)
-                    part = cadd(part, cmul(a0, cscale(cmulc(c, psi[n]), dx)));
+                    part = cadd(part, cmul(a0, cscale(cmulc(cur.chi[n], psi[n]), dx)));
                 }
             }
             for (int o = 1; o < p.nbp; o <<= 1) {
@@ -133,9 +176,7 @@ __global__ void __launch_bounds__(128) nlevel_sweep_kernel(NLevelParams p) {
                 part.y += __shfl_xor_sync(0xffffffffu, part.y, o);
             }
             if (l <= nt) {
-                const cd base = p.E_base[erun + l];
-                const double s = p.s_env[srun + l].x;
-                E = l > 0 ? cmk(base.x - s * part.y / h_lambda, base.y) : base;
+                E = l > 0 ? cmk(cur.base.x - cur.s * part.y / h_lambda, cur.base.y) : cur.base;
             } else {
                 E = cmk(0.0, 0.0);
             }
@@ -144,6 +185,9 @@ __global__ void __launch_bounds__(128) nlevel_sweep_kernel(NLevelParams p) {
             E_out[l] = E;
             if (p.write_E_base) p.E_base[erun + l] = E;
         }
+        // the only loads of the time loop; issued here, consumed one iteration later (no other load may share
+        // their scoreboard slot between here and the stores above, or the stores wait for HBM)
+        nxt = fetch(l + 1);
         if (l == 0 || !live) continue;
 
         // ---- level matrix for this field (rebuilt per step like hamil_2d.py:100-118) -------
@@ -170,11 +214,11 @@ __global__ void __launch_bounds__(128) nlevel_sweep_kernel(NLevelParams p) {
 #pragma unroll
         for (int n = 0; n < NL; ++n) {
             phi[n] = psi[n];
-            psi[n] = cmul(psi[n], dv[0]);
+            psi[n] = cmul(psi[n], NCH > 0 ? dv_r[0] : dv[0]);
         }
-        for (int j = 0; j < p.nch - 1; ++j) {
-            const double xpj = p.xp[j];
-            const cd dvj = dv[j + 1];
+        // residum (phys_base.py:98-111) in the reference's operand order: folding c1, c2, xp_j into the level
+        // matrix shortens the chain by 8 % but moves the ill-conditioned Jz configuration beyond 1e-9
+        auto order = [&](double xpj, cd dvj) {
             tri_apply<NL>(dg, up, lo, phi, tmp);
 #pragma unroll
             for (int n = 0; n < NL; ++n) {
@@ -184,6 +228,13 @@ __global__ void __launch_bounds__(128) nlevel_sweep_kernel(NLevelParams p) {
                 phi[n] = r;
                 psi[n] = cadd(psi[n], cmul(r, dvj));
             }
+        };
+        if (NCH > 0) {
+#pragma unroll
+            for (int j = 0; j < NCR - 1; ++j)
+                if (j < p.nch - 1) order(xp_r[j], dv_r[j + 1]);
+        } else {
+            for (int j = 0; j < p.nch - 1; ++j) order(p.xp[j], dv[j + 1]);
         }
         double nsum = 0.0;
         double nl[NL];
