@@ -577,3 +577,27 @@ if __name__ == "__main__":
     R = load_reference()
     for c in (sys.argv[1:] or list(CASES)):
         CASES[c](R)
+
+
+def case_shipped_confs(R=None):
+    """The ``user_conf`` dictionaries of the reference's functional tests (tests/functional_tests.py:77-1164) and the
+    reporter moduli they use, extracted with ``ast`` so that the full-length GPU runs use exactly those inputs."""
+    import ast
+    import json
+    src = open(os.path.join(REF, "tests", "functional_tests.py")).read()
+    out = {}
+    for node in ast.walk(ast.parse(src)):
+        if isinstance(node, ast.FunctionDef) and node.name.startswith("test_"):
+            entry = {}
+            for st in node.body:
+                if isinstance(st, ast.Assign) and isinstance(st.targets[0], ast.Name):
+                    name = st.targets[0].id
+                    if name in ("user_conf", "mod_fileout", "lmin", "imod_fileout", "imin"):
+                        entry[name] = ast.literal_eval(st.value)
+            out[node.name[5:]] = entry
+    with open(os.path.join(HERE, "shipped_confs.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print("wrote shipped_confs.json", sorted(out))
+
+
+CASES["shipped_confs"] = case_shipped_confs
