@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the propagation hot path (BASELINE.json metric: wavefunction grid-pt*timesteps/s).
 
-Workload (config.workload = "krotov_batch_np2048"): BASELINE config 5 -- per GPU ``--runs`` independent
+Workload (config.workload = "krotov_batch_8192x2048"): BASELINE config 5 -- per GPU ``--runs`` independent
 two-level Krotov problems on a 2048-point FFT grid, nch = 64 interpolation points, ``--nt`` time steps.
 One bench "step" is one Krotov iteration of the whole batch: forward sweep with the in-kernel field
 update from the stored backward trajectory, goal overlaps, chi(T) construction, backward sweep
@@ -91,7 +91,7 @@ def run_reference_arm(a):
     line = {"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1e3 * wall / max(a.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "krotov_batch_np2048", "np": NP_, "nch": NCH, "nlevs": NLEVS,
+            "config": {"workload": "krotov_batch_8192x2048", "np": NP_, "nch": NCH, "nlevs": NLEVS,
                        "impl_note": "numpy port of the reference path (oracle/qc_oracle.py); the reference is pure Python and /root/reference does not travel"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -268,7 +268,7 @@ def run_gpu_arm(a):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "krotov_batch_np2048", "runs_per_gpu": B, "np": NP_, "nlevs": NLEVS, "nch": NCH,
+                "config": {"workload": "krotov_batch_8192x2048", "runs_per_gpu": B, "np": NP_, "nlevs": NLEVS, "nch": NCH,
                            "nt": nt, "step": "one Krotov iteration (forward + backward sweep) of every run",
                            "l2": "working set (trajectories + state, %.1f GB) exceeds L2" % (
                                (2 * (nt + 1) * B * NP_ * 16 + 3 * B * 2 * NP_ * 16) / 1e9)},
@@ -288,7 +288,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--runs", type=int, default=4144, help="independent runs per GPU (28 x 148 SMs)")
+    ap.add_argument("--runs", type=int, default=8288,
+                    help="independent runs per GPU: the 8192 of BASELINE config 5 rounded up to 56 x 148 SMs")
     ap.add_argument("--nt", type=int, default=16, help="time steps per sweep")
     ap.add_argument("--cpu-steps", type=int, default=96, help="time steps each host process propagates for the CPU figure")
     ap.add_argument("--no-cpu", action="store_true")
