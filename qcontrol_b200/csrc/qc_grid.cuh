@@ -18,12 +18,14 @@
 // reordering pass is needed and the k-space multiply runs on the permuted layout.
 //
 // Synchronisation (N >= 512): the two levels are separate groups of warps that only meet at the coupling
-// term.  Each level synchronises its own transposes on a private named barrier; phi is handed over with a
-// full / released pair of named barriers (bar.arrive / bar.sync), so neither level waits for the other
-// unless it is a whole polynomial order ahead.
+// term.  Each level synchronises its own transposes on a private named barrier; phi is handed over through
+// two buffers (order parity) with a full / released pair of named barriers each (bar.arrive / bar.sync), so
+// a level waits for the other one only when it is more than a whole polynomial order ahead (+5 % over a
+// single hand-over buffer; forcing a half-order skew between the levels on top of that changed nothing).
 //
 // History of this kernel with ncu evidence: profiles/r01a (twiddle tables in shared memory, 0.41 of the
-// FP64 peak), r01c (register power chains, 0.48), r01d/r01e (TMEM accumulator and tables, 0.52).
+// FP64 peak), r01c (register power chains, 0.48), r01d/r01e (TMEM accumulator and tables, 0.52), r01g (one
+// transpose buffer + double-buffered hand-over, 0.555).
 #pragma once
 #include <cstdint>
 
@@ -81,10 +83,12 @@ struct GridCfg {
     static constexpr int MAXCH = 128;
     static constexpr bool NAMED = TPL >= 32;    // a level is made of whole warps: per-level named barriers
     static constexpr int TM_COLS = NTHREADS > 128 ? 512 : 256;   // 256 TMEM columns per warp slot
-    // shared memory (complex elements): per level transpose buffers A, B and the phi hand-over S ;
+    // shared memory (complex elements): per level ONE transpose buffer (forward and inverse passes use it in turn:
+    // every element is either private to an R3-lane group or read by the thread that wrote it, except across the two
+    // level barriers) and TWO phi hand-over buffers, so that the levels may run up to one polynomial order apart;
     // then dv, xp and 32 doubles of reduction scratch (the last one carries the TMEM base address)
     static constexpr size_t SMEM_BYTES =
-        sizeof(cd) * (size_t)(2 * (2 * BUF + N)) + sizeof(double) * (size_t)(3 * MAXCH + 32 + LC_STRIDE + LS_COUNT);
+        sizeof(cd) * (size_t)(2 * (BUF + 2 * N)) + sizeof(double) * (size_t)(3 * MAXCH + 32 + LC_STRIDE + LS_COUNT);
 };
 
 // skewed position of element (k2, n3) inside a lane group's private 16*R3 region
@@ -188,11 +192,11 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
     const int tid = threadIdx.x;
     const int lev = tid / TPL;
     const int t = tid - lev * TPL;
-    cd *bufA = sm + lev * (2 * BUF + N);
-    cd *bufB = bufA + BUF;
-    cd *stash = bufB + BUF;
-    const cd *stash_other = sm + (1 - lev) * (2 * BUF + N) + 2 * BUF;
-    cd *s_dv = sm + 2 * (2 * BUF + N);
+    cd *bufA = sm + lev * (BUF + 2 * N);
+    cd *bufB = bufA;
+    cd *stash0 = bufA + BUF;
+    const cd *stash0_other = sm + (1 - lev) * (BUF + 2 * N) + BUF;
+    cd *s_dv = sm + 2 * (BUF + 2 * N);
     double *s_xp = reinterpret_cast<double *>(s_dv + C::MAXCH);
     double *s_red = s_xp + C::MAXCH;              // 32 doubles of reduction scratch
     double *s_lc = s_red + 32;                    // local control: the run's state / constants ...
@@ -202,9 +206,10 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
     if ((int)blockIdx.x >= p.run_count || run >= p.batch) return;
     const int k1p = t / R3;       // k1' : which pass-1 output row this thread transforms in pass 2
     const int n3p = t % R3;       // n3' (also the lane's index c inside its group in pass 3)
-    // named barrier ids: 1,2 level-local transposes; 3,4 "phi of level n is available"; 5,6 "... released"
-    const int BAR_LEVEL = 1 + lev, BAR_FULL_OWN = 3 + lev, BAR_FULL_OTH = 4 - lev, BAR_REL_OWN = 5 + lev,
-              BAR_REL_OTH = 6 - lev;
+    // named barrier ids: 1,2 level-local transposes; 3..6 "phi of level n, order parity p is available";
+    // 7..10 "... has been read" (one pair per hand-over buffer, so arrive / sync alternate strictly on each id)
+    const int BAR_LEVEL = 1 + lev, BAR_FULL_OWN = 3 + 2 * lev, BAR_FULL_OTH = 3 + 2 * (1 - lev), BAR_REL_OWN = 7 + 2 * lev,
+              BAR_REL_OTH = 7 + 2 * (1 - lev);
 
     const long long prun = (long long)p.poly_stride * run;
     for (int i = tid; i < p.nch; i += C::NTHREADS) {
@@ -354,12 +359,15 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
             const cd dvj = s_dv[j + 1];
             // hand phi over to the other level (shared memory) once it has read the previous one, and keep
             // an own copy in TMEM for the pointwise phase
-            if (NAMED && j > 0) bar_sync(BAR_REL_OWN, C::NTHREADS);
+            const int par = j & 1;
+            cd *stash = stash0 + par * N;
+            const cd *stash_other = stash0_other + par * N;
+            if (NAMED && j > 1) bar_sync(BAR_REL_OWN + par, C::NTHREADS);     // buffer `par` was last used two orders ago
 #pragma unroll
             for (int n1 = 0; n1 < 16; ++n1) stash[t + TPL * n1] = a[n1];
 #pragma unroll
             for (int c4 = 0; c4 < 16; c4 += 4) tmem_store_c4(t_phi + c4 * 4, a + c4);
-            if (NAMED) bar_arrive(BAR_FULL_OWN, C::NTHREADS);   // producer side of a named barrier (no fence needed)
+            if (NAMED) bar_arrive(BAR_FULL_OWN + par, C::NTHREADS);   // producer side of a named barrier (no fence needed)
             // pass 1 : DFT over n1, twiddle w_N^(k1*t), transpose
             {
                 TmemTwiddles tw(t_tw1);
@@ -390,6 +398,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
             if (R3 > 1) {
 #pragma unroll
                 for (int q = 0; q < Q; ++q) dft<R3, true>(a + q * R3);
+                __syncwarp();                 // the group's forward reads of this row are done
 #pragma unroll
                 for (int e = 0; e < 16; ++e)
                     bufB[k1p * S1 + pos2<R3, Q>(n3p * Q + e / R3, e % R3)] = a[e];
@@ -411,7 +420,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
             }
             // pointwise part (hamil_2d.py:60-71, phys_base.py:98-111) and accumulation (phys_base.py:170-172),
             // in chunks of four grid points: psi and own phi from TMEM, the other level's phi from shared memory
-            if (NAMED) bar_sync(BAR_FULL_OTH, C::NTHREADS);
+            if (NAMED) bar_sync(BAR_FULL_OTH + par, C::NTHREADS);
             tmem_wait_st();
 #pragma unroll
             for (int c4 = 0; c4 < 16; c4 += 4) {
@@ -441,7 +450,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
                 tmem_store_c4(t_psi + c4 * 4, acc4);
             }
             if (NAMED) {
-                if (j < last_j) bar_arrive(BAR_REL_OTH, C::NTHREADS);
+                if (j + 2 <= last_j) bar_arrive(BAR_REL_OTH + par, C::NTHREADS);
             } else {
                 __syncthreads();                                                   // (#3) hand-over buffer reuse
             }
@@ -486,14 +495,14 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
             //      fitter.py:598-623); the two levels meet through the hand-over buffer -----------------------
             if (LOCAL) {
 #pragma unroll
-                for (int n1 = 0; n1 < 16; ++n1) stash[t + TPL * n1] = psi[n1];
+                for (int n1 = 0; n1 < 16; ++n1) stash0[t + TPL * n1] = psi[n1];
                 __syncthreads();
                 double q[4] = {0.0, 0.0, 0.0, 0.0};
                 if (lev == 0) {
                     const double *v0 = p.v + p.v_stride * run, *v1 = v0 + N;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const cd u = stash_other[t + TPL * i];
+                        const cd u = stash0_other[t + TPL * i];
                         const double qr = psi[i].x * u.x + psi[i].y * u.y, qi = psi[i].x * u.y - psi[i].y * u.x;
                         const double w = v0[t + TPL * i] - v1[t + TPL * i];
                         q[0] += qr; q[1] += qi; q[2] += qr * w; q[3] += qi * w;
