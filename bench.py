@@ -153,8 +153,12 @@ def run_gpu_arm(a):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.current_stream().cuda_stream
-    ctx = engine.Context(local, stream)
+    # One explicit stream for everything: the library launches on it and the timing events are recorded on it.
+    # (torch's default stream has handle 0, which qc_create reads as "create your own stream": events recorded
+    # on torch's default stream would then not wait for the library's kernels.)
+    tstream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(tstream)
+    ctx = engine.Context(local, tstream.cuda_stream)
     B, nt = a.runs, a.nt
 
     pbs = krotov_batch(B, NP_, nt, NCH, seed=12345 + rank)
@@ -192,13 +196,16 @@ def run_gpu_arm(a):
     sampler.start()
     launches0 = ctx.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
+    ev0.record(tstream)
+    ctx.timer_start()
     for _ in range(a.steps):
         gc = krotov_iteration()
-    ev1.record()
+    ev1.record(tstream)
+    lib_ms = ctx.timer_stop()                 # the library's own cudaEvent pair on the same stream (cross-check)
     barrier()
     launches = ctx.launches - launches0
     ms = ev0.elapsed_time(ev1)
+    assert abs(ms - lib_ms) <= 0.02 * ms + 0.5, ("timing events disagree", ms, lib_ms)
     sampler.stop_flag = True
     sampler.join()
     if world > 1:
