@@ -140,3 +140,46 @@ def test_abi_error_behaviour(ctx):
     with pytest.raises(QcError):
         pl.set_control(1.0, 99)                                       # nt > nt_max
     pl.close()
+
+
+@pytest.mark.parametrize("nlevs,aug", [(3, "x"), (5, "x"), (6, "z"), (7, "x"), (8, "x")])
+def test_unit_transform_level_counts(ctx, nlevs, aug):
+    """Every instantiation of the N-level kernel (2 ... 8 levels, nb = nlevs basis vectors coupled by the field
+    sum; BH_X and BH_Z matrices) through a short unitary-transformation optimisation against the oracle.  h_lambda
+    is chosen where the oracle itself moves by < 2e-12 under a 3e-16 perturbation of psi0 (with 5e-3 the 5-level
+    loop moves by 30-50 %: DESIGN.md, conditioning), so 1e-8 relative holds."""
+    from qcontrol_b200 import control
+    user = conf_ut_jx(150, 2, nlevs=nlevs, T=3.0e-13)
+    user["lf_aug_type"] = aug
+    user["fitter"]["h_lambda"] = 0.5 if aug == "x" else 5e8
+    user["fitter"]["propagation"]["nch"] = 16 if nlevs >= 6 else 8
+    pb = qo.make_problem(user, apply_auto=True)
+    ref = _rows(qo.Fitter(pb).run())
+    nb = control.NLevelBatch([pb, pb], ctx=ctx)
+    hist = nb.run_unit_transform()
+    got = _rows(hist[0])
+    assert got.shape == ref.shape
+    assert np.allclose(got[1:], ref[1:], rtol=1e-8, atol=1e-12), (nlevs, got - ref)
+    assert np.array_equal(_rows(hist[0]), _rows(hist[1]))
+    nb.close()
+
+
+def test_two_level_model_without_grid(ctx):
+    """hamil_type "two_levels" (hamil_2d.py:76-97): constant diagonal, complex coupling -E_full / -conj(E_full),
+    propagated by the N-level kernel; prescribed field, whole run against the oracle."""
+    from qcontrol_b200 import control
+    user = {"task_type": "trans_wo_control", "pot_type": "none", "wf_type": "const", "hamil_type": "two_levels",
+            "init_guess": "gauss", "init_guess_hf": "exp", "nb": 1, "nlevs": 2, "T": 4e-13, "np": 1, "L": 1.0, "Du": 300.0,
+            "fitter": {"impulses_number": 1, "hf_hide": False, "mod_log": 500,
+                       "propagation": {"nch": 16, "nt": 400, "E0": 60.0, "t0": 2e-13, "sigma": 6e-14, "nu_L": 0.9e13}}}
+    pb = qo.make_problem(user)
+    recs = []
+    fit = qo.Fitter(pb, on_step=lambda pid, v, st: recs.append(st.psi.copy()))
+    ref = _rows(fit.run())
+    nb = control.NLevelBatch([pb, pb], ctx=ctx)
+    hist = nb.run_prescribed()
+    assert np.allclose(_rows(hist[0]), ref, rtol=1e-9, atol=1e-12), _rows(hist[0]) - ref
+    out = nb.plan.get_state()
+    assert np.abs(out[0, 0] - recs[-1]).max() <= 1e-11
+    assert abs(abs(out[0, 0, 1, 0]) ** 2 - 0.5) < 0.5 and abs(out[0, 0, 1, 0]) > 1e-3     # population really moved
+    nb.close()
