@@ -68,7 +68,7 @@ typedef struct qc_plan qc_plan;
 
 typedef struct {
     int32_t hamil;      /* qc_hamil                                                  */
-    int32_t np;         /* grid points: 256..2048 (power of two) for NONTRIV, 1 else */
+    int32_t np;         /* grid points: 256..4096 (power of two) for NONTRIV (4096: two-CTA cluster per run), 1 else */
     int32_t nlevs;      /* 2 for NONTRIV/TWO_LEVELS; 2..8 for BH_X/BH_Z/QUBIT        */
     int32_t nb;         /* basis vectors per run (1 for NONTRIV)                     */
     int32_t nch;        /* interpolation points (power of two, <= 128)               */

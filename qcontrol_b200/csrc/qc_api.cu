@@ -51,6 +51,7 @@ struct qc_context {
     cudaEvent_t aux_ev[3];
     bool aux_ready;
     long long launches;
+    int sm_count;
     int live_plans;      // plans that still point at this context
     bool released;       // qc_destroy was called while plans were alive: freed with the last plan
 };
@@ -408,6 +409,7 @@ extern "C" int32_t qc_create(int32_t device, void *stream, qc_context **out) {
                     prop.major, prop.minor);
     qc_context *c = new qc_context();
     c->device = device;
+    c->sm_count = prop.multiProcessorCount;
     c->launches = 0;
     c->live_plans = 0;
     c->aux_ready = false;
@@ -499,8 +501,8 @@ extern "C" int32_t qc_plan_create(qc_context *ctx, const qc_plan_desc *desc, qc_
         return fail(QC_ERR_ARG, "qc_plan_create: nch=%d must be a power of two in [2,128]", d.nch);
     const bool grid = d.hamil == QC_HAMIL_NONTRIV;
     if (grid) {
-        if (!is_pow2(d.np) || d.np < 256 || d.np > 2048)
-            return fail(QC_ERR_ARG, "qc_plan_create: grid plans need np in {256,512,1024,2048}, got %d", d.np);
+        if (!is_pow2(d.np) || d.np < 256 || d.np > 4096)
+            return fail(QC_ERR_ARG, "qc_plan_create: grid plans need np in {256,512,1024,2048,4096}, got %d", d.np);
         if (d.nlevs != 2 || d.nb != 1)
             return fail(QC_ERR_ARG, "qc_plan_create: the FFT-grid Hamiltonian has nlevs=2, nb=1 (task_manager.py:925-932)");
     } else {
@@ -686,17 +688,33 @@ extern "C" int32_t qc_set_control(qc_plan *pl, const double *ctl, int32_t batche
 // ---------------------------------------------------------------------------
 // sweeps
 // ---------------------------------------------------------------------------
-template <int LOG2N, bool LOCAL = false>
+template <int LOG2N, bool LOCAL = false, bool CL = false>
 static int32_t launch_grid(qc_plan *pl, const qc::GridParams &gp, cudaStream_t stream) {
-    typedef qc::GridCfg<LOG2N> C;
+    typedef qc::GridCfg<LOG2N, CL> C;
     static bool attr_done[64] = {false};
     const int dev = pl->ctx->device;
     if (!attr_done[dev & 63]) {
-        QC_CUDA(cudaFuncSetAttribute(qc::grid_sweep_kernel<LOG2N, LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        QC_CUDA(cudaFuncSetAttribute(qc::grid_sweep_kernel<LOG2N, LOCAL, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)C::SMEM_BYTES));
         attr_done[dev & 63] = true;
     }
-    qc::grid_sweep_kernel<LOG2N, LOCAL><<<gp.run_count, C::NTHREADS, C::SMEM_BYTES, stream>>>(gp);
+    if constexpr (CL) {                              // one cluster of two CTAs (one level each) per run
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2u * (unsigned)gp.run_count);
+        cfg.blockDim = dim3(C::NTHREADS);
+        cfg.dynamicSmemBytes = C::SMEM_BYTES;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        QC_CUDA(cudaLaunchKernelEx(&cfg, qc::grid_sweep_kernel<LOG2N, LOCAL, CL>, gp));
+    } else {
+        qc::grid_sweep_kernel<LOG2N, LOCAL, CL><<<gp.run_count, C::NTHREADS, C::SMEM_BYTES, stream>>>(gp);
+    }
     pl->ctx->launches++;
     QC_CUDA(cudaGetLastError());
     return QC_OK;
@@ -779,6 +797,19 @@ static int32_t run_sweep(qc_plan *pl, const qc_sweep_args *a, bool single_step, 
                 case 11: return launch_grid<11, true>(pl, g, lst);
             }
             return fail(QC_ERR_ARG, "qc_sweep: unsupported np");
+        }
+        // cluster form (two SMs per run): the only form for np = 4096; at np = 2048 it shortens a step by 11 % when
+        // the batch cannot fill the GPU anyway (237 -> 209 us); below that the cluster barrier costs more than the
+        // second SM brings (np = 1024: 133 -> 160 us).  QC_GRID_CLUSTER=0/1 overrides the heuristic (tests).
+        bool cluster = pl->log2n == 12 || (pl->log2n == 11 && g.run_count * 2 <= pl->ctx->sm_count);
+        if (const char *e = getenv("QC_GRID_CLUSTER")) cluster = pl->log2n == 12 || (pl->log2n >= 9 && atoi(e) != 0);
+        if (cluster) {
+            switch (pl->log2n) {
+                case 9: return launch_grid<9, false, true>(pl, g, lst);
+                case 10: return launch_grid<10, false, true>(pl, g, lst);
+                case 11: return launch_grid<11, false, true>(pl, g, lst);
+                case 12: return launch_grid<12, false, true>(pl, g, lst);
+            }
         }
         switch (pl->log2n) {
             case 8: return launch_grid<8>(pl, g, lst);

@@ -27,6 +27,8 @@
 // FP64 peak), r01c (register power chains, 0.48), r01d/r01e (TMEM accumulator and tables, 0.52), r01g (one
 // transpose buffer + double-buffered hand-over, 0.555).
 #pragma once
+#include <cooperative_groups.h>
+
 #include <cstdint>
 
 #include "qc_fft.cuh"
@@ -71,24 +73,28 @@ struct GridParams {
     const double *lc_rdiag;      // [nch] reciprocal pivots
 };
 
-template <int LOG2N>
+// CL = false: one CTA holds both levels of a run.  CL = true: a cluster of two CTAs, one level each, on two SMs --
+// the only form for np = 4096 (a level alone fills the registers and shared memory of an SM) and the
+// low-latency form for batches too small to fill the GPU; the levels talk through distributed shared memory.
+template <int LOG2N, bool CL = false>
 struct GridCfg {
     static constexpr int N = 1 << LOG2N;
     static constexpr int TPL = N / 16;          // threads per level
-    static constexpr int R3 = N / 256;          // third radix (1,2,4,8)
+    static constexpr int R3 = N / 256;          // third radix (1,2,4,8,16)
     static constexpr int Q = 16 / R3;           // R3-point DFTs per thread in pass 3
     static constexpr int S1 = TPL + (R3 < 8 ? R3 : 0);   // padded row stride of the transpose buffers
     static constexpr int BUF = 16 * S1;         // complex elements per transpose buffer
-    static constexpr int NTHREADS = 2 * TPL;
+    static constexpr int NLEV_CTA = CL ? 1 : 2; // levels per CTA
+    static constexpr int NTHREADS = NLEV_CTA * TPL;
     static constexpr int MAXCH = 128;
-    static constexpr bool NAMED = TPL >= 32;    // a level is made of whole warps: per-level named barriers
+    static constexpr bool NAMED = !CL && TPL >= 32;   // a level is made of whole warps: per-level named barriers
     static constexpr int TM_COLS = NTHREADS > 128 ? 512 : 256;   // 256 TMEM columns per warp slot
     // shared memory (complex elements): per level ONE transpose buffer (forward and inverse passes use it in turn:
     // every element is either private to an R3-lane group or read by the thread that wrote it, except across the two
     // level barriers) and TWO phi hand-over buffers, so that the levels may run up to one polynomial order apart;
     // then dv, xp and 32 doubles of reduction scratch (the last one carries the TMEM base address)
     static constexpr size_t SMEM_BYTES =
-        sizeof(cd) * (size_t)(2 * (BUF + 2 * N)) + sizeof(double) * (size_t)(3 * MAXCH + 32 + LC_STRIDE + LS_COUNT);
+        sizeof(cd) * (size_t)(NLEV_CTA * (BUF + 2 * N)) + sizeof(double) * (size_t)(3 * MAXCH + 32 + LC_STRIDE + LS_COUNT);
 };
 
 // skewed position of element (k2, n3) inside a lane group's private 16*R3 region
@@ -182,33 +188,71 @@ __device__ __forceinline__ void level_sums(double val, double *s_red, int tid, d
     __syncthreads();
 }
 
-template <int LOG2N, bool LOCAL = false>
-__global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel(GridParams p) {
-    typedef GridCfg<LOG2N> C;
+// ---- cluster form: split-phase cluster barrier and sums over the two CTAs ----------------------------------
+__device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// Sum `val` over the threads of this CTA (= one level) and fetch the partner CTA's sum through distributed
+// shared memory; every thread gets (sum of level 0, sum of level 1).  Two full cluster barriers.
+template <int NTHREADS>
+__device__ __forceinline__ void cluster_sums(double val, double *s_red, int tid, int lev, double &sum0, double &sum1) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+    if ((tid & 31) == 0) s_red[tid >> 5] = val;
+    __syncthreads();
+    double own = 0.0;
+#pragma unroll
+    for (int g = 0; g < NTHREADS / 32; ++g) own += s_red[g];
+    if (tid == 0) s_red[16] = own;
+    cl_arrive();
+    cl_wait();
+    const double *remote = cooperative_groups::this_cluster().map_shared_rank(s_red + 16, 1 - lev);
+    const double oth = *remote;
+    cl_arrive();
+    cl_wait();
+    sum0 = lev == 0 ? own : oth;
+    sum1 = lev == 0 ? oth : own;
+}
+
+template <int LOG2N, bool LOCAL = false, bool CL = false>
+__global__ void __launch_bounds__(GridCfg<LOG2N, CL>::NTHREADS, 1) grid_sweep_kernel(GridParams p) {
+    static_assert(!(LOCAL && CL), "local control runs in the single-CTA form");
+    typedef GridCfg<LOG2N, CL> C;
     constexpr int N = C::N, TPL = C::TPL, R3 = C::R3, Q = C::Q, S1 = C::S1, BUF = C::BUF;
     constexpr bool NAMED = C::NAMED;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd *sm = reinterpret_cast<cd *>(smem_raw);
     const int tid = threadIdx.x;
-    const int lev = tid / TPL;
-    const int t = tid - lev * TPL;
-    cd *bufA = sm + lev * (BUF + 2 * N);
+    const int lev = CL ? (int)cooperative_groups::this_cluster().block_rank() : tid / TPL;
+    const int t = CL ? tid : tid - lev * TPL;
+    cd *bufA = sm + (CL ? 0 : lev) * (BUF + 2 * N);
     cd *bufB = bufA;
-    cd *stash0 = bufA + BUF;
-    const cd *stash0_other = sm + (1 - lev) * (BUF + 2 * N) + BUF;
-    cd *s_dv = sm + 2 * (BUF + 2 * N);
+    // hand-over buffers: in the cluster form a level PUSHES its phi into the partner CTA's shared memory (remote
+    // stores are fire-and-forget), so that the reads in the pointwise phase stay local
+    cd *stash0 = CL ? cooperative_groups::this_cluster().map_shared_rank(bufA + BUF, 1 - lev) : bufA + BUF;
+    const cd *stash0_other = CL ? bufA + BUF : sm + (1 - lev) * (BUF + 2 * N) + BUF;
+    cd *s_dv = sm + C::NLEV_CTA * (BUF + 2 * N);
     double *s_xp = reinterpret_cast<double *>(s_dv + C::MAXCH);
     double *s_red = s_xp + C::MAXCH;              // 32 doubles of reduction scratch
     double *s_lc = s_red + 32;                    // local control: the run's state / constants ...
     double *s_ls = s_lc + LC_STRIDE;              // ... and the scalars of the current step
 
-    const int run = p.run_first + blockIdx.x;
-    if ((int)blockIdx.x >= p.run_count || run >= p.batch) return;
+    const int slot = CL ? (int)blockIdx.x / 2 : (int)blockIdx.x;     // cluster-uniform
+    const int run = p.run_first + slot;
+    if (slot >= p.run_count || run >= p.batch) return;
+    auto level_sync = [&]() {                     // all threads of this thread's level
+        if (NAMED) bar_sync(1 + lev, TPL); else __syncthreads();
+    };
+    auto both_sums = [&](double val, double &s0, double &s1) {
+        if (CL) cluster_sums<C::NTHREADS>(val, s_red, tid, lev, s0, s1);
+        else level_sums<C::NTHREADS, TPL>(val, s_red, tid, s0, s1);
+    };
+    const bool writer = tid == 0 && (!CL || lev == 0);               // the one thread that writes per-run scalars
     const int k1p = t / R3;       // k1' : which pass-1 output row this thread transforms in pass 2
     const int n3p = t % R3;       // n3' (also the lane's index c inside its group in pass 3)
     // named barrier ids: 1,2 level-local transposes; 3..6 "phi of level n, order parity p is available";
     // 7..10 "... has been read" (one pair per hand-over buffer, so arrive / sync alternate strictly on each id)
-    const int BAR_LEVEL = 1 + lev, BAR_FULL_OWN = 3 + 2 * lev, BAR_FULL_OTH = 3 + 2 * (1 - lev), BAR_REL_OWN = 7 + 2 * lev,
+    const int BAR_FULL_OWN = 3 + 2 * lev, BAR_FULL_OTH = 3 + 2 * (1 - lev), BAR_REL_OWN = 7 + 2 * lev,
               BAR_REL_OTH = 7 + 2 * (1 - lev);
 
     const long long prun = (long long)p.poly_stride * run;
@@ -334,11 +378,11 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
                 }
             }
             double t0s, t1s;
-            level_sums<C::NTHREADS, TPL>(part, s_red, tid, t0s, t1s);
+            both_sums(part, t0s, t1s);
             const double tot = t0s + t1s;
             E = -2.0 * (tot * dx) / h_lambda;
         }
-        if (tid == 0 && !p.single_step) {
+        if (writer && !p.single_step) {
             E_out[l] = cmk(E, LOCAL ? s_lc[LC_FM] : 0.0);      // local control: the multiplier rides in the imaginary slot
             if (p.write_E_base) p.E_base[erun + l] = cmk(E, 0.0);
         }
@@ -368,12 +412,16 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
 #pragma unroll
             for (int c4 = 0; c4 < 16; c4 += 4) tmem_store_c4(t_phi + c4 * 4, a + c4);
             if (NAMED) bar_arrive(BAR_FULL_OWN + par, C::NTHREADS);   // producer side of a named barrier (no fence needed)
+            // cluster form: one split-phase cluster barrier per order is the whole protocol -- the partner waits for
+            // it before reading, and since the buffers alternate, this level's wait of order j+1 already implies
+            // that the partner has finished reading buffer `par` of order j
+            if (CL) cl_arrive();
             // pass 1 : DFT over n1, twiddle w_N^(k1*t), transpose
             {
                 TmemTwiddles tw(t_tw1);
                 dft16_table_out<false>(a, tw, [&](int k1, cd val) { bufA[k1 * S1 + t] = val; });
             }
-            if (NAMED) bar_sync(BAR_LEVEL, TPL); else __syncthreads();              // (#1)
+            level_sync();                                                           // (#1)
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) a[n2] = bufA[k1p * S1 + n2 * R3 + n3p];
             // pass 2 : DFT over n2, twiddle w_{16 R3}^(k2*n3), transpose inside the R3-lane group
@@ -412,7 +460,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
             if (R3 == 1) dft16<true>(a);
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) bufB[k1p * S1 + n2 * R3 + n3p] = a[n2];
-            if (NAMED) bar_sync(BAR_LEVEL, TPL); else __syncthreads();              // (#2)
+            level_sync();                                                           // (#2)
             // inverse pass 1 -> kinetic term (already scaled by c1) at x = t + TPL*n1
             {
                 TmemTwiddles tw(t_tw1);
@@ -421,6 +469,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
             // pointwise part (hamil_2d.py:60-71, phys_base.py:98-111) and accumulation (phys_base.py:170-172),
             // in chunks of four grid points: psi and own phi from TMEM, the other level's phi from shared memory
             if (NAMED) bar_sync(BAR_FULL_OTH + par, C::NTHREADS);
+            if (CL) cl_wait();
             tmem_wait_st();
 #pragma unroll
             for (int c4 = 0; c4 < 16; c4 += 4) {
@@ -451,7 +500,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
             }
             if (NAMED) {
                 if (j + 2 <= last_j) bar_arrive(BAR_REL_OTH + par, C::NTHREADS);
-            } else {
+            } else if (!CL) {
                 __syncthreads();                                                   // (#3) hand-over buffer reuse
             }
         }
@@ -472,10 +521,10 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
         }
         if (!p.single_step) {
             double n0, n1s;
-            level_sums<C::NTHREADS, TPL>(nrm, s_red, tid, n0, n1s);
+            both_sums(nrm, n0, n1s);
             n0 *= dx;
             n1s *= dx;
-            if (tid == 0) {
+            if (writer) {
                 p.norms[run * 2 + 0] = n0;
                 p.norms[run * 2 + 1] = n1s;
             }
@@ -544,6 +593,10 @@ __global__ void __launch_bounds__(GridCfg<LOG2N>::NTHREADS, 1) grid_sweep_kernel
     if (LOCAL) {
         __syncthreads();
         if (tid < LC_NSTATE) p.lc[(long long)run * LC_STRIDE + tid] = s_lc[tid];
+    }
+    if (CL) {                 // the partner may still be reading this CTA's hand-over buffer
+        cl_arrive();
+        cl_wait();
     }
     tmem_wait_st();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -109,7 +109,7 @@ def test_abi_error_behaviour(ctx):
     """Errors are return codes with a message (-> QcError), never a silent fallback or a crash."""
     from qcontrol_b200 import engine
     from qcontrol_b200._lib import QcError
-    for kw, frag in ((dict(np_=300), "np in"), (dict(np_=4096), "np in"), (dict(nch=48), "power of two"), (dict(nb=2), "nlevs=2, nb=1"),
+    for kw, frag in ((dict(np_=300), "np in"), (dict(np_=8192), "np in"), (dict(np_=128), "np in"), (dict(nch=48), "power of two"), (dict(nb=2), "nlevs=2, nb=1"),
                      (dict(batch=0), "batch=0")):
         args = dict(hamil=engine.HAMIL_NONTRIV, np_=512, nlevs=2, nb=1, nch=64, batch=2, nt_max=4)
         args.update(kw)
@@ -183,3 +183,22 @@ def test_two_level_model_without_grid(ctx):
     assert np.abs(out[0, 0] - recs[-1]).max() <= 1e-11
     assert abs(abs(out[0, 0, 1, 0]) ** 2 - 0.5) < 0.5 and abs(out[0, 0, 1, 0]) > 1e-3     # population really moved
     nb.close()
+
+
+def test_np4096_krotov_vs_oracle(ctx):
+    """np = 4096 (beyond every shipped configuration): a level alone fills one SM, so a run is a
+    cluster of two CTAs coupled through distributed shared memory.  Two Krotov iterations against the oracle."""
+    from qcontrol_b200 import control
+    user = conf_krotov(30, 1, np_=4096)
+    user["L"] = 20.0            # the grid spacing of the shipped np = 1024 box: same energy window, converged polynomial
+    pb = qo.make_problem(user)
+    ref = qo.Fitter(pb).run()
+    gb = control.GridBatch([pb, pb], ctx=ctx)
+    hist = gb.run_krotov()
+    got, want = _rows(hist[0]), _rows(ref)
+    assert got.shape == want.shape
+    assert np.allclose(got, want, rtol=1e-9, atol=1e-12), got - want
+    for r, q in zip(hist[0], ref):
+        assert np.allclose(r.E_tlist, q.E_tlist, rtol=1e-9, atol=1e-9 * np.abs(q.E_tlist).max())
+    assert np.array_equal(_rows(hist[0]), _rows(hist[1]))
+    gb.close()
