@@ -557,6 +557,15 @@ class NLevelBatch(_BatchBase):
             base_rows.append(br)
         pl.set_s_env(self._pad(s_rows))
         it = 0
+        # throughput mode bookkeeping as arrays over the batch (rows are materialised after the loop)
+        q_all = np.array([float(p.q) for p in self.pbs])
+        mid1_all = np.array([p.iter_mid_1 for p in self.pbs])
+        mid2_all = np.array([p.iter_mid_2 for p in self.pbs])
+        lim_all = np.array([-p.nb * p.nb * float(p.q) for p in self.pbs])
+        Fgoal_all = np.array([float(p.F_goal) for p in self.pbs])
+        eps_all = np.array([float(p.epsilon) for p in self.pbs])
+        itmax_all = np.array([p.iter_max if iter_max is None else iter_max for p in self.pbs])
+        records = []
         self.ctx.synchronize()
         t_loop = time.perf_counter()
         while True:
@@ -611,17 +620,33 @@ class NLevelBatch(_BatchBase):
                     F_all = -gc.real.sum(axis=1)
                 else:
                     F_all = -(gc * np.conj(gc)).real.sum(axis=1)
+            if not keep_fields:
+                active = ~done
+                J_all = F_all - h_lambda * h_lambda * E_int_all
+                goal_close_abs = np.where(active, np.abs(tau), goal_close_abs)
+                records.append((it, active, goal_close_abs.copy(), F_all, E_int_all, J_all))
+                guard = active & (q_all != 0.0) & (it >= 1)
+                at1 = guard & (it == mid1_all)
+                F_mid_1 = np.where(at1, F_all, F_mid_1)
+                at2 = guard & ~at1 & (it == mid2_all)
+                diverged = at2 & ((F_mid_1 > lim_all) | (F_all > lim_all) | (F_mid_1 < F_all))     # fitter.py:550-560
+                for b in np.nonzero(diverged)[0]:
+                    self.errors[b] = "The calculation is probably going to diverge.  Stopping the run..."
+                reached = (np.abs(F_all - Fgoal_all) <= eps_all) | ((it >= itmax_all) & (itmax_all != -1))
+                done = done | diverged | (active & reached)
+                if done.all():
+                    break
+                it += 1
+                continue
             stop_all = True
             for b, p in enumerate(self.pbs):
                 if done[b]:
                     continue
-                if keep_fields:
+                if True:
                     Et = E[b, :p.nt + 1]
                     E_int = field_integral(Et, p.t_step)
                     F = _F_value(p.F_type, gc[b], p.nb)
                     E_list = _shown_fields(Et)
-                else:
-                    E_int, F, E_list = np.complex128(E_int_all[b]), np.complex128(F_all[b]), None
                 J = F.real - h_lambda[b] * h_lambda[b] * E_int.real
                 goal_close_abs[b] = abs(gc[b].sum())
                 hist[b].append(IterRow(it, float(goal_close_abs[b]), float(F.real), float(E_int.real), float(J), E_list))
@@ -644,4 +669,7 @@ class NLevelBatch(_BatchBase):
             it += 1
         self.ctx.synchronize()
         self.loop_wall_s = time.perf_counter() - t_loop       # iteration loop only (set-up excluded)
+        for k, active, gca, F_all, E_int_all, J_all in records:
+            for b in np.nonzero(active)[0]:
+                hist[b].append(IterRow(k, float(gca[b]), float(F_all[b]), float(E_int_all[b]), float(J_all[b]), None))
         return hist
