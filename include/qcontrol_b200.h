@@ -227,6 +227,27 @@ int32_t qc_record_state(qc_plan *plan, int32_t buffer, int32_t index, int32_t le
  * H2D of psi, nsteps prescribed-field steps, D2H of psi, all on the context's stream. Synchronous. */
 int32_t qc_propagate_host(qc_plan *plan, const qc_sweep_args *args, const double *psi_in, double *psi_out);
 
+/* ---- two-dimensional grids (synthetic extension: "hamil_2d 512x512" of BASELINE config 5; the reference has no
+ * 2-D operator) ----------------------------------------------------------------------------------
+ * One-level wavefunctions psi[batch][n][n] (row-major, y contiguous) under H = T_x + T_y + V(x,y), propagated by the
+ * same Newton polynomial as phys_base.prop_cpu (phys_base.py:129-178) with the 2-D analogue of hamil_cpu
+ * (phys_base.py:39-70): T_x = ifft_x(akx2 * fft_x .), T_y likewise.  n = 512. */
+typedef struct qc_plan2d qc_plan2d;
+int32_t qc_plan2d_create(qc_context *ctx, int32_t n, int32_t nch, int32_t batch, qc_plan2d **out);
+int32_t qc_plan2d_destroy(qc_plan2d *plan);
+/* v[batch|1][n][n] potential, akx2_re[n] / aky2_re[n] kinetic multipliers (math_base.initak scaled as in
+ * task_manager.py:501-504), dxdy = area element of the norm */
+int32_t qc_plan2d_set_static(qc_plan2d *plan, const double *v, int32_t v_batched, const double *akx2_re,
+                             const double *aky2_re, double dxdy);
+/* xp[nch], dv[nch] complex (math_base.points), sc = {emin, emax, t_sc} */
+int32_t qc_plan2d_set_poly(qc_plan2d *plan, const double *xp, const double *dv, const double *sc);
+int32_t qc_plan2d_set_state(qc_plan2d *plan, const double *psi);
+int32_t qc_plan2d_get_state(qc_plan2d *plan, double *psi);
+/* nsteps time steps of every wavefunction; renorm != 0: divide by sqrt(|<psi|psi>|) after each (propagation.py:450-459) */
+int32_t qc_plan2d_sweep(qc_plan2d *plan, int32_t nsteps, int32_t renorm);
+/* norms[batch]: <psi|psi> of the last step before renormalisation */
+int32_t qc_plan2d_get_norms(qc_plan2d *plan, double *norms);
+
 #ifdef __cplusplus
 }
 #endif

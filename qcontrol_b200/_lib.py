@@ -20,6 +20,8 @@ SYMBOLS = (
     "qc_set_static", "qc_set_poly", "qc_set_state", "qc_get_state", "qc_set_step_scalars", "qc_set_control",
     "qc_sweep", "qc_prop_step", "qc_apply_hamil", "qc_set_instr_grid", "qc_instrument", "qc_set_local_control", "qc_get_local_state", "qc_set_local_state", "qc_get_fields", "qc_field_integral", "qc_get_norms", "qc_snapshot_set", "qc_snapshot_load", "qc_goal_overlap", "qc_krotov_terminal",
     "qc_get_traj", "qc_record_state", "qc_propagate_host",
+    "qc_plan2d_create", "qc_plan2d_destroy", "qc_plan2d_set_static", "qc_plan2d_set_poly", "qc_plan2d_set_state",
+    "qc_plan2d_get_state", "qc_plan2d_sweep", "qc_plan2d_get_norms",
 )
 
 
@@ -75,6 +77,14 @@ def _load():
         "qc_set_local_control": (i32, [vp, dp, dp, dp]),
         "qc_get_local_state": (i32, [vp, dp]),
         "qc_set_local_state": (i32, [vp, dp]),
+        "qc_plan2d_create": (i32, [vp, i32, i32, i32, C.POINTER(vp)]),
+        "qc_plan2d_destroy": (i32, [vp]),
+        "qc_plan2d_set_static": (i32, [vp, dp, i32, dp, dp, C.c_double]),
+        "qc_plan2d_set_poly": (i32, [vp, dp, dp, dp]),
+        "qc_plan2d_set_state": (i32, [vp, dp]),
+        "qc_plan2d_get_state": (i32, [vp, dp]),
+        "qc_plan2d_sweep": (i32, [vp, i32, i32]),
+        "qc_plan2d_get_norms": (i32, [vp, dp]),
         "qc_get_fields": (i32, [vp, dp]),
         "qc_field_integral": (i32, [vp, dp]),
         "qc_get_norms": (i32, [vp, dp]),

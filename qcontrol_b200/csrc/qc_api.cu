@@ -12,6 +12,7 @@
 
 #include "../../include/qcontrol_b200.h"
 #include "qc_grid.cuh"
+#include "qc_grid2d.cuh"
 #include "qc_nlevel.cuh"
 
 using qc::cd;
@@ -1209,5 +1210,159 @@ extern "C" int32_t qc_propagate_host(qc_plan *pl, const qc_sweep_args *args, con
         QC_CUDA(cudaStreamWaitEvent(st, ctx->aux_ev[1 + i], 0));
     }
     QC_CUDA(cudaStreamSynchronize(st));
+    return QC_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// two-dimensional grids (kernel C, qc_grid2d.cuh)
+// ---------------------------------------------------------------------------
+struct qc_plan2d {
+    qc_context *ctx;
+    int n, nch, batch;
+    int v_batched = 0;
+    bool static_set = false, poly_set = false;
+    double emin = 0, emax = 0, t_sc = 0, dxdy = 0;
+    DevBuf<cd> psi, phi, tmp, dv, tw1, tw2;
+    DevBuf<double> v, kinx, kiny, xp, norm_acc, norms;
+};
+static const int kWavesPerLaunch = 2;        // 2 x 64 CTAs of a cooperative launch on 148 SMs
+
+extern "C" int32_t qc_plan2d_create(qc_context *ctx, int32_t n, int32_t nch, int32_t batch, qc_plan2d **out) {
+    if (!ctx || !out) return fail(QC_ERR_ARG, "qc_plan2d_create: NULL argument");
+    if (n != 512) return fail(QC_ERR_ARG, "qc_plan2d_create: the 2-D stepper is built for 512 x 512 grids, got n=%d", n);
+    if (!is_pow2(nch) || nch < 2 || nch > 128) return fail(QC_ERR_ARG, "qc_plan2d_create: nch=%d must be a power of two in [2,128]", nch);
+    if (batch < 1) return fail(QC_ERR_ARG, "qc_plan2d_create: batch=%d", batch);
+    QC_CUDA(cudaSetDevice(ctx->device));
+    int coop = 0;
+    QC_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+    if (!coop) return fail(QC_ERR_CUDA, "qc_plan2d_create: the device does not support cooperative launches");
+    qc_plan2d *pl = new qc_plan2d();
+    pl->ctx = ctx;
+    pl->n = n; pl->nch = nch; pl->batch = batch;
+    const size_t nn = (size_t)n * n;
+    const int waves = batch < kWavesPerLaunch ? batch : kWavesPerLaunch;
+    cudaError_t e = cudaSuccess;
+    auto chk = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    chk(pl->psi.alloc(nn * batch));
+    chk(pl->phi.alloc(nn * waves));
+    chk(pl->tmp.alloc(nn * waves));
+    chk(pl->dv.alloc(nch));
+    chk(pl->xp.alloc(nch));
+    chk(pl->kinx.alloc(n));
+    chk(pl->kiny.alloc(n));
+    chk(pl->norms.alloc(batch));
+    std::vector<cd> t1, t2;
+    fill_twiddles(qc::G2_LOG2N, t1, t2);
+    chk(pl->tw1.alloc(t1.size()));
+    chk(pl->tw2.alloc(t2.size()));
+    if (e == cudaSuccess) chk(cudaMemcpy(pl->tw1.p, t1.data(), t1.size() * sizeof(cd), cudaMemcpyHostToDevice));
+    if (e == cudaSuccess) chk(cudaMemcpy(pl->tw2.p, t2.data(), t2.size() * sizeof(cd), cudaMemcpyHostToDevice));
+    if (e == cudaSuccess) chk(cudaMemset(pl->norms.p, 0, batch * sizeof(double)));
+    if (e != cudaSuccess) {
+        delete pl;
+        return fail(QC_ERR_CUDA, "qc_plan2d_create: %s", cudaGetErrorString(e));
+    }
+    ctx->live_plans++;
+    *out = pl;
+    return QC_OK;
+}
+
+extern "C" int32_t qc_plan2d_destroy(qc_plan2d *pl) {
+    if (!pl) return QC_OK;
+    cudaSetDevice(pl->ctx->device);
+    cudaStreamSynchronize(pl->ctx->stream);
+    pl->psi.release(); pl->phi.release(); pl->tmp.release(); pl->dv.release(); pl->tw1.release(); pl->tw2.release();
+    pl->v.release(); pl->kinx.release(); pl->kiny.release(); pl->xp.release(); pl->norm_acc.release(); pl->norms.release();
+    qc_context *ctx = pl->ctx;
+    delete pl;
+    if (--ctx->live_plans == 0 && ctx->released) context_free(ctx);
+    return QC_OK;
+}
+
+extern "C" int32_t qc_plan2d_set_static(qc_plan2d *pl, const double *v, int32_t v_batched, const double *akx2_re,
+                                        const double *aky2_re, double dxdy) {
+    if (!pl || !v || !akx2_re || !aky2_re) return fail(QC_ERR_ARG, "qc_plan2d_set_static: NULL argument");
+    if (!(dxdy > 0.0)) return fail(QC_ERR_ARG, "qc_plan2d_set_static: dxdy=%g", dxdy);
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    const size_t nn = (size_t)pl->n * pl->n;
+    const size_t count = nn * (v_batched ? pl->batch : 1);
+    if (pl->v.n != count) QC_CUDA(pl->v.alloc(count));
+    QC_CUDA(cudaMemcpyAsync(pl->v.p, v, count * sizeof(double), cudaMemcpyHostToDevice, pl->ctx->stream));
+    QC_CUDA(cudaMemcpyAsync(pl->kinx.p, akx2_re, pl->n * sizeof(double), cudaMemcpyHostToDevice, pl->ctx->stream));
+    QC_CUDA(cudaMemcpyAsync(pl->kiny.p, aky2_re, pl->n * sizeof(double), cudaMemcpyHostToDevice, pl->ctx->stream));
+    QC_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+    pl->v_batched = v_batched ? 1 : 0;
+    pl->dxdy = dxdy;
+    pl->static_set = true;
+    return QC_OK;
+}
+
+extern "C" int32_t qc_plan2d_set_poly(qc_plan2d *pl, const double *xp, const double *dv, const double *sc) {
+    if (!pl || !xp || !dv || !sc) return fail(QC_ERR_ARG, "qc_plan2d_set_poly: NULL argument");
+    if (!(sc[1] > sc[0])) return fail(QC_ERR_ARG, "qc_plan2d_set_poly: emax (%g) must exceed emin (%g)", sc[1], sc[0]);
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    QC_CUDA(cudaMemcpyAsync(pl->xp.p, xp, pl->nch * sizeof(double), cudaMemcpyHostToDevice, pl->ctx->stream));
+    QC_CUDA(cudaMemcpyAsync(pl->dv.p, dv, pl->nch * sizeof(cd), cudaMemcpyHostToDevice, pl->ctx->stream));
+    QC_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+    pl->emin = sc[0]; pl->emax = sc[1]; pl->t_sc = sc[2];
+    pl->poly_set = true;
+    return QC_OK;
+}
+
+extern "C" int32_t qc_plan2d_set_state(qc_plan2d *pl, const double *psi) {
+    if (!pl || !psi) return fail(QC_ERR_ARG, "qc_plan2d_set_state: NULL argument");
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    QC_CUDA(cudaMemcpyAsync(pl->psi.p, psi, pl->psi.n * sizeof(cd), cudaMemcpyHostToDevice, pl->ctx->stream));
+    QC_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+    return QC_OK;
+}
+
+extern "C" int32_t qc_plan2d_get_state(qc_plan2d *pl, double *psi) {
+    if (!pl || !psi) return fail(QC_ERR_ARG, "qc_plan2d_get_state: NULL argument");
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    QC_CUDA(cudaMemcpyAsync(psi, pl->psi.p, pl->psi.n * sizeof(cd), cudaMemcpyDeviceToHost, pl->ctx->stream));
+    QC_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+    return QC_OK;
+}
+
+extern "C" int32_t qc_plan2d_get_norms(qc_plan2d *pl, double *norms) {
+    if (!pl || !norms) return fail(QC_ERR_ARG, "qc_plan2d_get_norms: NULL argument");
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    QC_CUDA(cudaMemcpyAsync(norms, pl->norms.p, pl->batch * sizeof(double), cudaMemcpyDeviceToHost, pl->ctx->stream));
+    QC_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+    return QC_OK;
+}
+
+extern "C" int32_t qc_plan2d_sweep(qc_plan2d *pl, int32_t nsteps, int32_t renorm) {
+    if (!pl) return fail(QC_ERR_ARG, "qc_plan2d_sweep: NULL argument");
+    if (!pl->static_set || !pl->poly_set) return fail(QC_ERR_STATE, "qc_plan2d_sweep: qc_plan2d_set_static / qc_plan2d_set_poly first");
+    if (nsteps < 1) return fail(QC_ERR_ARG, "qc_plan2d_sweep: nsteps=%d", nsteps);
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    typedef qc::Grid2DCfg C;
+    static bool attr_done[64] = {false};
+    if (!attr_done[pl->ctx->device & 63]) {
+        QC_CUDA(cudaFuncSetAttribute(qc::grid2d_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+        attr_done[pl->ctx->device & 63] = true;
+    }
+    const size_t acc = (size_t)nsteps * kWavesPerLaunch * C::TILES;
+    if (pl->norm_acc.n < acc) QC_CUDA(pl->norm_acc.alloc(acc));
+    for (int first = 0; first < pl->batch; first += kWavesPerLaunch) {
+        const int count = pl->batch - first < kWavesPerLaunch ? pl->batch - first : kWavesPerLaunch;
+        qc::Grid2DParams g;
+        memset(&g, 0, sizeof g);
+        g.n = pl->n; g.nch = pl->nch; g.nsteps = nsteps; g.renorm = renorm;
+        g.wave_first = first; g.wave_count = count;
+        g.psi = pl->psi.p; g.phi = pl->phi.p; g.tmp = pl->tmp.p;
+        g.v = pl->v.p; g.v_stride = pl->v_batched ? (long long)pl->n * pl->n : 0;
+        g.kinx = pl->kinx.p; g.kiny = pl->kiny.p; g.tw1 = pl->tw1.p; g.tw2 = pl->tw2.p;
+        g.xp = pl->xp.p; g.dv = pl->dv.p; g.emin = pl->emin; g.emax = pl->emax; g.t_sc = pl->t_sc; g.dxdy = pl->dxdy;
+        g.norm_acc = pl->norm_acc.p; g.norms = pl->norms.p;
+        void *args[] = {&g};
+        QC_CUDA(cudaLaunchCooperativeKernel((const void *)qc::grid2d_sweep_kernel, dim3(C::TILES * count), dim3(C::NTHREADS),
+                                            args, C::SMEM_BYTES, pl->ctx->stream));
+        pl->ctx->launches++;
+    }
+    QC_CUDA(cudaGetLastError());
     return QC_OK;
 }

@@ -288,3 +288,57 @@ class Plan:
         check(lib.qc_instrument(self._h, _ptr(Ea.view(np.float64)), float(two_m), int(psi0_slot), int(psif_slot),
                                 _ptr(out)))
         return out
+
+
+class Plan2D:
+    """Device-resident batch of one-level wavefunctions on an n x n grid (qc_plan2d_*, kernel C): the synthetic
+    "hamil_2d 512 x 512" extension.  psi[batch][n][n], row-major (y contiguous)."""
+
+    def __init__(self, ctx: Context, n: int, nch: int, batch: int):
+        self.ctx = ctx
+        self.n, self.nch, self.batch = int(n), int(nch), int(batch)
+        self._h = C.c_void_p()
+        check(lib.qc_plan2d_create(ctx._h, self.n, self.nch, self.batch, C.byref(self._h)))
+        ctx._plans.add(self)
+        self.state_shape = (self.batch, self.n, self.n)
+
+    def close(self):
+        if self._h:
+            lib.qc_plan2d_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_static(self, v, akx2_re, aky2_re, dxdy):
+        v = _f64(v)
+        vb = v.ndim == 3
+        _f64(v, ((self.batch,) if vb else ()) + (self.n, self.n))
+        kx, ky = _f64(akx2_re, (self.n,)), _f64(aky2_re, (self.n,))
+        check(lib.qc_plan2d_set_static(self._h, _ptr(v), int(vb), _ptr(kx), _ptr(ky), float(dxdy)))
+
+    def set_poly(self, xp, dv, emin, emax, t_sc):
+        xp = _f64(xp, (self.nch,))
+        dv = _c128(dv, (self.nch,))
+        sc = np.array([emin, emax, t_sc], np.float64)
+        check(lib.qc_plan2d_set_poly(self._h, _ptr(xp), _ptr(dv.view(np.float64)), _ptr(sc)))
+
+    def set_state(self, psi):
+        psi = _c128(psi, self.state_shape)
+        check(lib.qc_plan2d_set_state(self._h, _ptr(psi.view(np.float64))))
+
+    def get_state(self):
+        out = np.empty(self.state_shape, np.complex128)
+        check(lib.qc_plan2d_get_state(self._h, _ptr(out.view(np.float64))))
+        return out
+
+    def sweep(self, nsteps=1, renorm=True):
+        check(lib.qc_plan2d_sweep(self._h, int(nsteps), int(bool(renorm))))
+
+    def get_norms(self):
+        out = np.empty(self.batch, np.float64)
+        check(lib.qc_plan2d_get_norms(self._h, _ptr(out)))
+        return out

@@ -239,3 +239,39 @@ def test_shipped_pi_pulse_table(golden):
     ref = s["pi_pulse__iter_tab"]
     assert tab.shape == ref.shape
     assert np.allclose(tab, ref, rtol=1e-9, atol=1e-12)
+
+
+def test_grid2d_separable():
+    """The 2-D restatement (oracle/qc_oracle2d.py, no reference counterpart) against the pinned 1-D path: for
+    V(x,y) = V1(x) + V2(y) and a product state, converged 2-D steps equal the outer product of 1-D steps."""
+    from oracle import qc_oracle2d as q2
+    N, L = 64, 10.0
+    dx = L / (N - 1)
+    x = (np.arange(N) - (N - 1) / 2) * dx
+    ak = qo.initak(N, dx, 2, 1) * (-qo.HART_TO_CM / (2.0 * 0.5 * qo.DALT_TO_AU))
+    v1, v2 = 9000 * x ** 2 / 2, 5000 * (x - 0.3) ** 2 / 2
+    f = np.exp(-(x - 0.5) ** 2 / 0.8).astype(complex)
+    g = (np.exp(-(x + 0.4) ** 2 / 1.1) * np.exp(2j * x)).astype(complex)
+    f /= np.sqrt(dx * np.sum(abs(f) ** 2))
+    g /= np.sqrt(dx * np.sum(abs(g) ** 2))
+    v = v1[:, None] + v2[None, :]
+    dt, nch, steps = 4e-18, 64, 5
+    emax, emin = q2.energy_window_2d(v, ak, ak, N)
+    psi = f[:, None] * g[None, :]
+    for _ in range(steps):
+        psi, nrm = q2.step_2d(psi, v, ak, ak, nch, dt, dx * dx, emin, emax)
+        assert abs(nrm - 1.0) < 1e-10
+
+    def p1(state, vv):
+        pb = qo.Problem(hamil="ntriv", ntriv=1, np_=N, nlevs=2, nb=1, dx=dx, v=np.stack([vv, vv]), vmin=np.zeros(2),
+                        akx2=ak, nch=nch)
+        em = float(vv.max() + abs(ak[N // 2 - 1]))
+        t_sc = dt * em * qo.CM_TO_ERG / 4 / qo.RED_PLANCK_H
+        st = np.stack([state, np.zeros_like(state)])
+        for _ in range(steps):
+            st = qo.newton_propagate(pb, st, t_sc, 0.0, em, np.float64(0.0), 0.0, np.float64(0.0))
+            st = st / np.sqrt(abs(np.vdot(st, st) * dx))
+        return st[0]
+
+    ref = p1(f, v1)[:, None] * p1(g, v2)[None, :]
+    assert np.sqrt(dx * dx * np.sum(abs(psi - ref) ** 2)) < 1e-12
