@@ -568,7 +568,9 @@ class NLevelBatch(_BatchBase):
         records = []
         self.ctx.synchronize()
         t_loop = time.perf_counter()
+        self.iter_marks = []                      # host clock at the start of every iteration (tools/bench_nlevel.py)
         while True:
+            self.iter_marks.append(time.perf_counter())
             # ---- backward sweep from the goal basis (fitter.py:241-249) ----------------------------
             pl.snapshot_load(1)
             pl.record_state(1, 0)
@@ -668,6 +670,7 @@ class NLevelBatch(_BatchBase):
                 break
             it += 1
         self.ctx.synchronize()
+        self.iter_marks.append(time.perf_counter())
         self.loop_wall_s = time.perf_counter() - t_loop       # iteration loop only (set-up excluded)
         for k, active, gca, F_all, E_int_all, J_all in records:
             for b in np.nonzero(active)[0]:

@@ -52,17 +52,20 @@ def main():
     for copies in a.copies:
         runs = pbs * copies
         nb = control.NLevelBatch(runs, ctx=ctx)
-        walls = {}
-        for n_it in (2, a.iters):                      # set-up cost is paid by both calls: the difference is the loop
-            nb.time_sweeps, nb.sweep_ms = True, 0.0
-            ctx.synchronize()
-            t0 = time.perf_counter()
-            hist = nb.run_unit_transform(iter_max=n_it - 1, keep_fields=False)
-            ctx.synchronize()
-            walls[n_it] = (nb.loop_wall_s, nb.sweep_ms * 1e-3, time.perf_counter() - t0)
-        d_it = a.iters - 2
-        d_wall = walls[a.iters][0] - walls[2][0]
-        d_sweep = walls[a.iters][1] - walls[2][1]
+        # one call; iteration 0 carries one-time work (field tables of the backward sweep, first-touch of the host
+        # arrays), so the rate is taken over iterations 1 ... iters-1 from the loop's own time marks
+        nb.time_sweeps, nb.sweep_ms = True, 0.0
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        hist = nb.run_unit_transform(iter_max=a.iters - 1, keep_fields=False)
+        ctx.synchronize()
+        total = time.perf_counter() - t0
+        marks = nb.iter_marks
+        assert len(marks) == a.iters + 1
+        d_it = a.iters - 1
+        d_wall = marks[-1] - marks[1]
+        d_sweep = nb.sweep_ms * 1e-3 * d_it / a.iters
+        walls = {2: (0.0, 0.0, total - (marks[-1] - marks[0]))}
         steps = sum(p.nt for p in runs) * 2 * d_it * runs[0].nb          # solver steps (per basis vector)
         traj_bytes = sum(p.nt for p in runs) * d_it * 2 * runs[0].nb * runs[0].nlevs * 16
         print(json.dumps({"workload": "ut_jx_Tsweep x%d" % copies, "runs": len(runs), "iterations_timed": d_it,
