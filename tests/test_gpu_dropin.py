@@ -223,3 +223,36 @@ def test_batch_entry_point(tmp_path):
         assert abs(float(fit_tab[1].split()[0]) - 100 * pb.t_step * 1e15) < 1e-6
         abs0 = (path.parent / "iter_0b" / "basis_0" / "tables" / "tab_abs_0.csv").read_text().strip().splitlines()
         assert len(abs0) == pb.nt // 100 + 1
+
+
+def test_newcheb_command_line(tmp_path):
+    """`python -m qcontrol_b200.newcheb --json_task T.json --json_rep R.json` (newcheb.py:612-690): the reference's
+    command line on a small substitution template; one output directory per variant, the summary table on stdout."""
+    import json
+    import subprocess
+    import sys
+    from tests.golden.gen_golden import conf_ut_jx
+    tpl = conf_ut_jx(1, 1)
+    tpl["run_id"] = "cli"
+    tpl["T"] = {"@SUBST:LIST": [2.0e-13, 3.0e-13, 2.6e-13]}
+    tpl["nt_auto"] = True
+    tpl["fitter"]["h_lambda"] = 5e-4
+    rep = {"fitter": {"out_path": str(tmp_path / "o_{input:$.run_id}" / "T={input:$.T}"), "plotting_flag": "tables_iter",
+                      "table.imin": -1, "propagation": {"table.mod_fileout": 100}}}
+    (tmp_path / "task.json").write_text(json.dumps(tpl))
+    (tmp_path / "rep.json").write_text(json.dumps(rep))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "qcontrol_b200.newcheb", "--json_task", str(tmp_path / "task.json"),
+                          "--json_rep", str(tmp_path / "rep.json"), "--seed_base", "1000"], cwd=root, capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.count("Job #") == 3 and "goal_close" in out.stdout
+    for T in (2.0e-13, 3.0e-13, 2.6e-13):
+        d = tmp_path / "o_cli" / ("T=%s" % T)
+        rows = (d / "tab_iter.csv").read_text().strip().splitlines()
+        assert [r.split()[0] for r in rows] == ["-1", "0", "1"]
+        assert not (d / "tab_iter_E.csv").exists()             # tables_iter: no field table (reporter.py:604-606)
+        assert (d / "table_inp_-1.txt").exists()
+    bad = subprocess.run([sys.executable, "-m", "qcontrol_b200.newcheb", "--json_task", str(tmp_path / "task.json")],
+                         cwd=root, capture_output=True, text=True, timeout=120)
+    assert bad.returncode == 2 and "Usage" in bad.stdout
