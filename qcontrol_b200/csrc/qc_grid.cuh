@@ -23,6 +23,10 @@
 // a level waits for the other one only when it is more than a whole polynomial order ahead (+5 % over a
 // single hand-over buffer; forcing a half-order skew between the levels on top of that changed nothing).
 //
+// Packed form (RPC > 0, np <= 512): RPC runs per CTA, the two levels of a run interleaved in every warp (lanes L and
+// L^16), the coupling term a warp shuffle in k space, one named barrier per run (np = 512) or none (np = 256):
+// eight warps per SM instead of two or four (0.26 -> 0.60 and 0.42 -> 0.51 of the FP64 peak).
+//
 // History of this kernel with ncu evidence: profiles/r01a (twiddle tables in shared memory, 0.41 of the
 // FP64 peak), r01c (register power chains, 0.48), r01d/r01e (TMEM accumulator and tables, 0.52), r01g (one
 // transpose buffer + double-buffered hand-over, 0.555).
@@ -76,7 +80,10 @@ struct GridParams {
 // CL = false: one CTA holds both levels of a run.  CL = true: a cluster of two CTAs, one level each, on two SMs --
 // the only form for np = 4096 (a level alone fills the registers and shared memory of an SM) and the
 // low-latency form for batches too small to fill the GPU; the levels talk through distributed shared memory.
-template <int LOG2N, bool CL = false>
+// RPC > 0: the PACKED form for small grids -- RPC runs per CTA so that a CTA has four warps (all four tensor-memory
+// lane quadrants in use) and an SM holds eight; the two levels of a run are interleaved inside every warp (lanes L
+// and L^16), see the kernel.
+template <int LOG2N, bool CL = false, int RPC = 0>
 struct GridCfg {
     static constexpr int N = 1 << LOG2N;
     static constexpr int TPL = N / 16;          // threads per level
@@ -85,16 +92,21 @@ struct GridCfg {
     static constexpr int S1 = TPL + (R3 < 8 ? R3 : 0);   // padded row stride of the transpose buffers
     static constexpr int BUF = 16 * S1;         // complex elements per transpose buffer
     static constexpr int NLEV_CTA = CL ? 1 : 2; // levels per CTA
-    static constexpr int NTHREADS = NLEV_CTA * TPL;
+    static constexpr bool PK = RPC > 0;
+    static constexpr int RT = 2 * TPL;          // threads per run (packed form)
+    static constexpr int NTHREADS = PK ? RPC * RT : NLEV_CTA * TPL;
     static constexpr int MAXCH = 128;
-    static constexpr bool NAMED = !CL && TPL >= 32;   // a level is made of whole warps: per-level named barriers
+    static constexpr bool NAMED = !CL && !PK && TPL >= 32;   // a level is made of whole warps: per-level named barriers
     static constexpr int TM_COLS = NTHREADS > 128 ? 512 : 256;   // 256 TMEM columns per warp slot
     // shared memory (complex elements): per level ONE transpose buffer (forward and inverse passes use it in turn:
     // every element is either private to an R3-lane group or read by the thread that wrote it, except across the two
     // level barriers) and TWO phi hand-over buffers, so that the levels may run up to one polynomial order apart;
     // then dv, xp and 32 doubles of reduction scratch (the last one carries the TMEM base address)
+    // packed form: per run two transpose buffers, dv, xp and 16 doubles of reduction scratch; then 32 doubles per CTA
+    static constexpr size_t RUN_BYTES = sizeof(cd) * (size_t)(2 * BUF + MAXCH) + sizeof(double) * (size_t)(MAXCH + 16);
     static constexpr size_t SMEM_BYTES =
-        sizeof(cd) * (size_t)(NLEV_CTA * (BUF + 2 * N)) + sizeof(double) * (size_t)(3 * MAXCH + 32 + LC_STRIDE + LS_COUNT);
+        PK ? RPC * RUN_BYTES + sizeof(double) * 32
+           : sizeof(cd) * (size_t)(NLEV_CTA * (BUF + 2 * N)) + sizeof(double) * (size_t)(3 * MAXCH + 32 + LC_STRIDE + LS_COUNT);
 };
 
 // skewed position of element (k2, n3) inside a lane group's private 16*R3 region
@@ -188,6 +200,35 @@ __device__ __forceinline__ void level_sums(double val, double *s_red, int tid, d
     __syncthreads();
 }
 
+// Packed form: lanes 0-15 of every warp belong to level 0, lanes 16-31 to level 1; a run is W warps that meet on
+// the run's own named barrier.
+template <int W>
+__device__ __forceinline__ void packed_sums(double val, double *s_red, int rtid, int bar_id, double &sum0, double &sum1) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+    const double oth = __shfl_xor_sync(0xffffffffu, val, 16);
+    const bool hi = (rtid >> 4) & 1;
+    const double a0 = hi ? oth : val, a1 = hi ? val : oth;      // this warp's share of the two level sums
+    if (W == 1) {
+        sum0 = a0;
+        sum1 = a1;
+        return;
+    }
+    if ((rtid & 31) == 0) {
+        s_red[2 * (rtid >> 5)] = a0;
+        s_red[2 * (rtid >> 5) + 1] = a1;
+    }
+    bar_sync(bar_id, 32 * W);
+    sum0 = 0.0;
+    sum1 = 0.0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        sum0 += s_red[2 * w];
+        sum1 += s_red[2 * w + 1];
+    }
+    bar_sync(bar_id, 32 * W);
+}
+
 // ---- cluster form: split-phase cluster barrier and sums over the two CTAs ----------------------------------
 __device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
@@ -214,40 +255,53 @@ __device__ __forceinline__ void cluster_sums(double val, double *s_red, int tid,
     sum1 = lev == 0 ? oth : own;
 }
 
-template <int LOG2N, bool LOCAL = false, bool CL = false>
-__global__ void __launch_bounds__(GridCfg<LOG2N, CL>::NTHREADS, 1) grid_sweep_kernel(GridParams p) {
+template <int LOG2N, bool LOCAL = false, bool CL = false, int RPC = 0>
+__global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC>::NTHREADS, 1) grid_sweep_kernel(GridParams p) {
     static_assert(!(LOCAL && CL), "local control runs in the single-CTA form");
-    typedef GridCfg<LOG2N, CL> C;
+    static_assert(!(RPC > 0 && (LOCAL || CL)), "the packed form exists for the plain single-CTA kernel only");
+    typedef GridCfg<LOG2N, CL, RPC> C;
     constexpr int N = C::N, TPL = C::TPL, R3 = C::R3, Q = C::Q, S1 = C::S1, BUF = C::BUF;
-    constexpr bool NAMED = C::NAMED;
+    constexpr bool NAMED = C::NAMED, PK = C::PK;
+    constexpr int RW = C::RT / 32;                // warps per run (packed form)
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cd *sm = reinterpret_cast<cd *>(smem_raw);
     const int tid = threadIdx.x;
-    const int lev = CL ? (int)cooperative_groups::this_cluster().block_rank() : tid / TPL;
-    const int t = CL ? tid : tid - lev * TPL;
-    cd *bufA = sm + (CL ? 0 : lev) * (BUF + 2 * N);
+    // packed form: run slot rslot of this CTA, thread rtid of the run; the two levels of grid point set t sit in
+    // lanes L and L^16 of one warp, so the coupling term is a warp shuffle (in k space, where both levels hold the
+    // same frequencies) instead of a shared-memory hand-over, and a run synchronises on its own named barrier
+    const int rslot = PK ? tid / C::RT : 0;
+    const int rtid = PK ? tid - rslot * C::RT : tid;
+    cd *sm = reinterpret_cast<cd *>(smem_raw + (PK ? rslot * C::RUN_BYTES : 0));
+    const int lev = CL ? (int)cooperative_groups::this_cluster().block_rank() : PK ? (rtid >> 4) & 1 : tid / TPL;
+    const int t = CL ? tid : PK ? (rtid & 15) | ((rtid >> 5) << 4) : tid - lev * TPL;
+    cd *bufA = sm + (CL ? 0 : lev) * (PK ? BUF : BUF + 2 * N);
     cd *bufB = bufA;
     // hand-over buffers: in the cluster form a level PUSHES its phi into the partner CTA's shared memory (remote
     // stores are fire-and-forget), so that the reads in the pointwise phase stay local
     cd *stash0 = CL ? cooperative_groups::this_cluster().map_shared_rank(bufA + BUF, 1 - lev) : bufA + BUF;
     const cd *stash0_other = CL ? bufA + BUF : sm + (1 - lev) * (BUF + 2 * N) + BUF;
-    cd *s_dv = sm + C::NLEV_CTA * (BUF + 2 * N);
+    cd *s_dv = sm + (PK ? 2 * BUF : C::NLEV_CTA * (BUF + 2 * N));
     double *s_xp = reinterpret_cast<double *>(s_dv + C::MAXCH);
     double *s_red = s_xp + C::MAXCH;              // 32 doubles of reduction scratch
     double *s_lc = s_red + 32;                    // local control: the run's state / constants ...
     double *s_ls = s_lc + LC_STRIDE;              // ... and the scalars of the current step
 
-    const int slot = CL ? (int)blockIdx.x / 2 : (int)blockIdx.x;     // cluster-uniform
-    const int run = p.run_first + slot;
-    if (slot >= p.run_count || run >= p.batch) return;
-    auto level_sync = [&]() {                     // all threads of this thread's level
-        if (NAMED) bar_sync(1 + lev, TPL); else __syncthreads();
+    const int slot = CL ? (int)blockIdx.x / 2 : PK ? (int)blockIdx.x * RPC + rslot : (int)blockIdx.x;     // cluster-uniform
+    // packed form: an empty run slot of the last CTA keeps its threads (they take part in the CTA-wide barriers
+    // around the tensor-memory allocation), reads the first run and does no step and no store
+    const bool valid = slot < p.run_count && p.run_first + slot < p.batch;
+    if (!PK && !valid) return;
+    const int run = valid ? p.run_first + slot : p.run_first;
+    auto level_sync = [&]() {                     // all threads of this thread's level (packed form: of the run)
+        if (PK) {
+            if (RW == 1) __syncwarp(); else bar_sync(1 + rslot, C::RT);
+        } else if (NAMED) bar_sync(1 + lev, TPL); else __syncthreads();
     };
     auto both_sums = [&](double val, double &s0, double &s1) {
         if (CL) cluster_sums<C::NTHREADS>(val, s_red, tid, lev, s0, s1);
+        else if (PK) packed_sums<RW>(val, s_red, rtid, 1 + rslot, s0, s1);
         else level_sums<C::NTHREADS, TPL>(val, s_red, tid, s0, s1);
     };
-    const bool writer = tid == 0 && (!CL || lev == 0);               // the one thread that writes per-run scalars
+    const bool writer = (PK ? rtid == 0 && valid : tid == 0) && (!CL || lev == 0);   // the one thread that writes per-run scalars
     const int k1p = t / R3;       // k1' : which pass-1 output row this thread transforms in pass 2
     const int n3p = t % R3;       // n3' (also the lane's index c inside its group in pass 3)
     // named barrier ids: 1,2 level-local transposes; 3..6 "phi of level n, order parity p is available";
@@ -256,7 +310,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL>::NTHREADS, 1) grid_sweep_ke
               BAR_REL_OTH = 7 + 2 * (1 - lev);
 
     const long long prun = (long long)p.poly_stride * run;
-    for (int i = tid; i < p.nch; i += C::NTHREADS) {
+    for (int i = rtid; i < p.nch; i += (PK ? C::RT : C::NTHREADS)) {
         s_xp[i] = p.xp[i];
         s_dv[i] = p.dv[prun * p.nch + i];
     }
@@ -296,7 +350,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL>::NTHREADS, 1) grid_sweep_ke
         for (int n1 = 0; n1 < 16; ++n1) psi[n1] = src[t + TPL * n1];
     }
     // ---- tensor memory: one warp allocates, everybody learns the base address ------------------------
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_red + 30);
+    uint32_t *s_tmem = PK ? reinterpret_cast<uint32_t *>(smem_raw + RPC * C::RUN_BYTES) : reinterpret_cast<uint32_t *>(s_red + 30);
     if (tid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          (uint32_t)__cvta_generic_to_shared(s_tmem)),
@@ -327,7 +381,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL>::NTHREADS, 1) grid_sweep_ke
     const int ov_lev = p.field_mode == 2 ? 1 : 0;
     const int last_j = p.nch - 2;
 
-    for (int l = p.l_first; l < p.l_first + p.nsteps && l <= nt; ++l) {
+    for (int l = p.l_first; l < p.l_first + p.nsteps && l <= nt && (!PK || valid); ++l) {
         const bool start_only = (l == 0);   // start(): only the initial field is evaluated (propagation.py:360-361)
         // ---- local control: this step's multiplier, energy window and Newton table (qc_local.cuh) ----
         if (LOCAL && !start_only) {
@@ -389,6 +443,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL>::NTHREADS, 1) grid_sweep_ke
         if (start_only) continue;
         const double cE = c1 * E;
         const double cEi = c1 * Ei;
+        const double cEk = cE / (double)N, cEik = cEi / (double)N;     // packed form: coupling applied before the inverse transform
 
         // ---- Newton recurrence (phys_base.py:158-172): phi = psi, psi <- dv0 * psi (parked in TMEM) -----
 #pragma unroll
@@ -407,8 +462,10 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL>::NTHREADS, 1) grid_sweep_ke
             cd *stash = stash0 + par * N;
             const cd *stash_other = stash0_other + par * N;
             if (NAMED && j > 1) bar_sync(BAR_REL_OWN + par, C::NTHREADS);     // buffer `par` was last used two orders ago
+            if (!PK) {
 #pragma unroll
-            for (int n1 = 0; n1 < 16; ++n1) stash[t + TPL * n1] = a[n1];
+                for (int n1 = 0; n1 < 16; ++n1) stash[t + TPL * n1] = a[n1];
+            }
 #pragma unroll
             for (int c4 = 0; c4 < 16; c4 += 4) tmem_store_c4(t_phi + c4 * 4, a + c4);
             if (NAMED) bar_arrive(BAR_FULL_OWN + par, C::NTHREADS);   // producer side of a named barrier (no fence needed)
@@ -441,8 +498,26 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL>::NTHREADS, 1) grid_sweep_ke
                 for (int q = 0; q < Q; ++q) dft<R3, false>(a + q * R3);
             }
             // k-space: kinetic multiplier (with c1 and the 1/N of the inverse transform folded in)
+            if (!PK) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) a[e] = cscale(a[e], kc[e]);
+                for (int e = 0; e < 16; ++e) a[e] = cscale(a[e], kc[e]);
+            } else {
+                // ... and the coupling -E * phi_other (hamil_2d.py:70-71): the partner lane holds the other level at
+                // the same frequencies; the transform is linear, so the term may join before the inverse passes
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    cd o, r;
+                    o.x = __shfl_xor_sync(0xffffffffu, a[e].x, 16);
+                    o.y = __shfl_xor_sync(0xffffffffu, a[e].y, 16);
+                    r.x = fma(kc[e], a[e].x, -cEk * o.x);
+                    r.y = fma(kc[e], a[e].y, -cEk * o.y);
+                    if (p.cplx_coupling) {           // orig=True form of hamil_2d.py:40-47
+                        r.x = fma(cEik, o.y, r.x);
+                        r.y = fma(-cEik, o.x, r.y);
+                    }
+                    a[e] = r;
+                }
+            }
             if (R3 > 1) {
 #pragma unroll
                 for (int q = 0; q < Q; ++q) dft<R3, true>(a + q * R3);
@@ -477,8 +552,10 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL>::NTHREADS, 1) grid_sweep_ke
                 tmem_ld16(t_psi + c4 * 4, rp);
                 tmem_ld16(t_phi + c4 * 4, rs);
                 cd oth4[4], own4[4], acc4[4];
+                if (!PK) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) oth4[i] = stash_other[t + TPL * (c4 + i)];
+                    for (int i = 0; i < 4; ++i) oth4[i] = stash_other[t + TPL * (c4 + i)];
+                }
                 tmem_wait_ld();
                 tmem_unpack_c4(rp, acc4);
                 tmem_unpack_c4(rs, own4);
@@ -487,11 +564,16 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL>::NTHREADS, 1) grid_sweep_ke
                     const int n1 = c4 + i;
                     const double dd = dcoef[n1] - xpj;
                     cd r;
-                    r.x = fma(dd, own4[i].x, fma(-cE, oth4[i].x, a[n1].x));
-                    r.y = fma(dd, own4[i].y, fma(-cE, oth4[i].y, a[n1].y));
-                    if (p.cplx_coupling) {           // orig=True form of hamil_2d.py:40-47 (uniform branch, off in sweeps)
-                        r.x = fma(cEi, oth4[i].y, r.x);
-                        r.y = fma(-cEi, oth4[i].x, r.y);
+                    if (PK) {                        // the coupling term is already inside a[]
+                        r.x = fma(dd, own4[i].x, a[n1].x);
+                        r.y = fma(dd, own4[i].y, a[n1].y);
+                    } else {
+                        r.x = fma(dd, own4[i].x, fma(-cE, oth4[i].x, a[n1].x));
+                        r.y = fma(dd, own4[i].y, fma(-cE, oth4[i].y, a[n1].y));
+                        if (p.cplx_coupling) {       // orig=True form of hamil_2d.py:40-47 (uniform branch, off in sweeps)
+                            r.x = fma(cEi, oth4[i].y, r.x);
+                            r.y = fma(-cEi, oth4[i].x, r.y);
+                        }
                     }
                     a[n1] = r;
                     acc4[i] = cfma(dvj, r, acc4[i]);
@@ -500,7 +582,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL>::NTHREADS, 1) grid_sweep_ke
             }
             if (NAMED) {
                 if (j + 2 <= last_j) bar_arrive(BAR_REL_OTH + par, C::NTHREADS);
-            } else if (!CL) {
+            } else if (!CL && !PK) {
                 __syncthreads();                                                   // (#3) hand-over buffer reuse
             }
         }
@@ -581,11 +663,13 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL>::NTHREADS, 1) grid_sweep_ke
                     }
                 }
             }
-        } else {
+        } else if (!PK) {
             __syncthreads();
+        } else {
+            level_sync();
         }
     }
-    {
+    if (!PK || valid) {
         cd *dst = p.psi + ((long long)run * 2 + lev) * N;
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) dst[t + TPL * n1] = psi[n1];
