@@ -689,13 +689,13 @@ extern "C" int32_t qc_set_control(qc_plan *pl, const double *ctl, int32_t batche
 // ---------------------------------------------------------------------------
 // sweeps
 // ---------------------------------------------------------------------------
-template <int LOG2N, bool LOCAL = false, bool CL = false, int RPC = 0>
+template <int LOG2N, bool LOCAL = false, bool CL = false, int RPC = 0, bool ILV = false>
 static int32_t launch_grid(qc_plan *pl, const qc::GridParams &gp, cudaStream_t stream) {
-    typedef qc::GridCfg<LOG2N, CL, RPC> C;
+    typedef qc::GridCfg<LOG2N, CL, RPC, ILV> C;
     static bool attr_done[64] = {false};
     const int dev = pl->ctx->device;
     if (!attr_done[dev & 63]) {
-        QC_CUDA(cudaFuncSetAttribute(qc::grid_sweep_kernel<LOG2N, LOCAL, CL, RPC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        QC_CUDA(cudaFuncSetAttribute(qc::grid_sweep_kernel<LOG2N, LOCAL, CL, RPC, ILV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)C::SMEM_BYTES));
         attr_done[dev & 63] = true;
     }
@@ -715,7 +715,7 @@ static int32_t launch_grid(qc_plan *pl, const qc::GridParams &gp, cudaStream_t s
         QC_CUDA(cudaLaunchKernelEx(&cfg, qc::grid_sweep_kernel<LOG2N, LOCAL, CL>, gp));
     } else {
         const int ctas = RPC > 0 ? (gp.run_count + RPC - 1) / RPC : gp.run_count;
-        qc::grid_sweep_kernel<LOG2N, LOCAL, CL, RPC><<<ctas, C::NTHREADS, C::SMEM_BYTES, stream>>>(gp);
+        qc::grid_sweep_kernel<LOG2N, LOCAL, CL, RPC, ILV><<<ctas, C::NTHREADS, C::SMEM_BYTES, stream>>>(gp);
     }
     pl->ctx->launches++;
     QC_CUDA(cudaGetLastError());
@@ -813,16 +813,17 @@ static int32_t run_sweep(qc_plan *pl, const qc_sweep_args *a, bool single_step, 
                 case 12: return launch_grid<12, false, true>(pl, g, lst);
             }
         }
-        // packed form (np <= 512): several runs per CTA so that every SM holds eight warps, the levels interleaved in
-        // every warp (np = 256: 0.26 -> 0.60 of the FP64 peak, np = 512: 0.42 -> 0.51).  Batches that are resident all
-        // at once in the one-run-per-CTA form (two CTAs per SM) keep it: its single step is 4-12 % shorter.
+        // packed form (np <= 512): several runs per CTA so that every SM holds eight warps -- np = 256: four runs, the
+        // levels interleaved in every warp (0.26 -> 0.60 of the FP64 peak); np = 512: two runs, a level per warp
+        // (0.42 -> 0.52).  Batches that are resident all at once in the one-run-per-CTA form (two CTAs per SM) keep
+        // it: its single step is 4-12 % shorter.
         // QC_GRID_PACK=0/1 overrides the heuristic (tests run both forms).
         bool packed = pl->log2n <= 9 && g.run_count > 2 * pl->ctx->sm_count;
         if (const char *e = getenv("QC_GRID_PACK")) packed = pl->log2n <= 9 && atoi(e) != 0;
         if (packed) {
             switch (pl->log2n) {
-                case 8: return launch_grid<8, false, false, 4>(pl, g, lst);
-                case 9: return launch_grid<9, false, false, 2>(pl, g, lst);
+                case 8: return launch_grid<8, false, false, 4, true>(pl, g, lst);
+                case 9: return launch_grid<9, false, false, 2, false>(pl, g, lst);
             }
         }
         switch (pl->log2n) {

@@ -19,13 +19,18 @@
 //
 // Synchronisation (N >= 512): the two levels are separate groups of warps that only meet at the coupling
 // term.  Each level synchronises its own transposes on a private named barrier; phi is handed over through
-// two buffers (order parity) with a full / released pair of named barriers each (bar.arrive / bar.sync), so
-// a level waits for the other one only when it is more than a whole polynomial order ahead (+5 % over a
-// single hand-over buffer; forcing a half-order skew between the levels on top of that changed nothing).
+// two buffers (order parity) with one "available" named barrier each (bar.arrive by the producer, bar.sync by
+// the consumer), so a level waits for the other one only when it is more than a whole polynomial order ahead
+// (+5 % over a single hand-over buffer; forcing a half-order skew between the levels on top of that changed
+// nothing).  No "has been read" handshake is needed: a level passes its wait for the partner's order j+1 only
+// after the partner has finished order j, i.e. has read this level's buffer of order j, and that buffer is not
+// rewritten before order j+2 (dropping the handshake: +1.6 % at np = 2048).
 //
-// Packed form (RPC > 0, np <= 512): RPC runs per CTA, the two levels of a run interleaved in every warp (lanes L and
-// L^16), the coupling term a warp shuffle in k space, one named barrier per run (np = 512) or none (np = 256):
-// eight warps per SM instead of two or four (0.26 -> 0.60 and 0.42 -> 0.51 of the FP64 peak).
+// Packed form (RPC > 0, np <= 512): RPC runs per CTA, so that an SM holds eight warps instead of two or four.
+// np = 256 (ILV): four runs per CTA, the two levels of a run interleaved in one warp (lanes L and L^16), the coupling
+// term a warp shuffle in k space, no barrier wider than a warp (0.26 -> 0.60 of the FP64 peak).  np = 512: two runs
+// per CTA, a level per warp and the hand-over of the plain form with five named barriers per run (0.42 -> 0.52;
+// the interleaved layout measured 0.51 here, 0.51 against 0.56 at np = 1024 / 2048).
 //
 // History of this kernel with ncu evidence: profiles/r01a (twiddle tables in shared memory, 0.41 of the
 // FP64 peak), r01c (register power chains, 0.48), r01d/r01e (TMEM accumulator and tables, 0.52), r01g (one
@@ -83,7 +88,7 @@ struct GridParams {
 // RPC > 0: the PACKED form for small grids -- RPC runs per CTA so that a CTA has four warps (all four tensor-memory
 // lane quadrants in use) and an SM holds eight; the two levels of a run are interleaved inside every warp (lanes L
 // and L^16), see the kernel.
-template <int LOG2N, bool CL = false, int RPC = 0>
+template <int LOG2N, bool CL = false, int RPC = 0, bool ILV = false>
 struct GridCfg {
     static constexpr int N = 1 << LOG2N;
     static constexpr int TPL = N / 16;          // threads per level
@@ -102,8 +107,10 @@ struct GridCfg {
     // every element is either private to an R3-lane group or read by the thread that wrote it, except across the two
     // level barriers) and TWO phi hand-over buffers, so that the levels may run up to one polynomial order apart;
     // then dv, xp and 32 doubles of reduction scratch (the last one carries the TMEM base address)
-    // packed form: per run two transpose buffers, dv, xp and 16 doubles of reduction scratch; then 32 doubles per CTA
-    static constexpr size_t RUN_BYTES = sizeof(cd) * (size_t)(2 * BUF + MAXCH) + sizeof(double) * (size_t)(MAXCH + 16);
+    // packed form: per run two transpose buffers (level-per-warp layout: and the four hand-over buffers), dv, xp and
+    // 16 doubles of reduction scratch; then 32 doubles per CTA
+    static constexpr int LEVEL_ELEMS = ILV ? BUF : BUF + 2 * N;     // complex elements of shared memory per level
+    static constexpr size_t RUN_BYTES = sizeof(cd) * (size_t)(2 * LEVEL_ELEMS + MAXCH) + sizeof(double) * (size_t)(MAXCH + 16);
     static constexpr size_t SMEM_BYTES =
         PK ? RPC * RUN_BYTES + sizeof(double) * 32
            : sizeof(cd) * (size_t)(NLEV_CTA * (BUF + 2 * N)) + sizeof(double) * (size_t)(3 * MAXCH + 32 + LC_STRIDE + LS_COUNT);
@@ -229,6 +236,23 @@ __device__ __forceinline__ void packed_sums(double val, double *s_red, int rtid,
     bar_sync(bar_id, 32 * W);
 }
 
+// Packed form, level-per-warp layout: the first W/2 warps of a run are level 0, the others level 1.
+template <int W>
+__device__ __forceinline__ void packed_level_sums(double val, double *s_red, int rtid, int bar_id, double &sum0, double &sum1) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+    if ((rtid & 31) == 0) s_red[rtid >> 5] = val;
+    bar_sync(bar_id, 32 * W);
+    sum0 = 0.0;
+    sum1 = 0.0;
+#pragma unroll
+    for (int w = 0; w < W / 2; ++w) {
+        sum0 += s_red[w];
+        sum1 += s_red[W / 2 + w];
+    }
+    bar_sync(bar_id, 32 * W);
+}
+
 // ---- cluster form: split-phase cluster barrier and sums over the two CTAs ----------------------------------
 __device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
@@ -255,13 +279,18 @@ __device__ __forceinline__ void cluster_sums(double val, double *s_red, int tid,
     sum1 = lev == 0 ? oth : own;
 }
 
-template <int LOG2N, bool LOCAL = false, bool CL = false, int RPC = 0>
-__global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC>::NTHREADS, 1) grid_sweep_kernel(GridParams p) {
+template <int LOG2N, bool LOCAL = false, bool CL = false, int RPC = 0, bool ILV = false>
+__global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV>::NTHREADS, 1) grid_sweep_kernel(GridParams p) {
     static_assert(!(LOCAL && CL), "local control runs in the single-CTA form");
     static_assert(!(RPC > 0 && (LOCAL || CL)), "the packed form exists for the plain single-CTA kernel only");
-    typedef GridCfg<LOG2N, CL, RPC> C;
+    static_assert(!ILV || RPC > 0, "interleaved levels are a layout of the packed form");
+    static_assert(ILV || RPC == 0 || GridCfg<LOG2N>::TPL == 32, "packed level-per-warp layout: a level is one warp");
+    typedef GridCfg<LOG2N, CL, RPC, ILV> C;
     constexpr int N = C::N, TPL = C::TPL, R3 = C::R3, Q = C::Q, S1 = C::S1, BUF = C::BUF;
-    constexpr bool NAMED = C::NAMED, PK = C::PK;
+    constexpr bool PK = C::PK;
+    constexpr bool PKL = PK && !ILV;              // packed, a level per warp: shared-memory hand-over like the plain form
+    constexpr bool NAMED = C::NAMED || PKL;       // hand-over through full barriers (bar.arrive / bar.sync)
+    constexpr int HN = PK ? C::RT : C::NTHREADS;  // threads that meet on a hand-over barrier
     constexpr int RW = C::RT / 32;                // warps per run (packed form)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
@@ -271,15 +300,15 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC>::NTHREADS, 1) grid_swe
     const int rslot = PK ? tid / C::RT : 0;
     const int rtid = PK ? tid - rslot * C::RT : tid;
     cd *sm = reinterpret_cast<cd *>(smem_raw + (PK ? rslot * C::RUN_BYTES : 0));
-    const int lev = CL ? (int)cooperative_groups::this_cluster().block_rank() : PK ? (rtid >> 4) & 1 : tid / TPL;
-    const int t = CL ? tid : PK ? (rtid & 15) | ((rtid >> 5) << 4) : tid - lev * TPL;
-    cd *bufA = sm + (CL ? 0 : lev) * (PK ? BUF : BUF + 2 * N);
+    const int lev = CL ? (int)cooperative_groups::this_cluster().block_rank() : ILV ? (rtid >> 4) & 1 : rtid / TPL;
+    const int t = CL ? tid : ILV ? (rtid & 15) | ((rtid >> 5) << 4) : rtid - lev * TPL;
+    cd *bufA = sm + (CL ? 0 : lev) * (ILV ? BUF : BUF + 2 * N);
     cd *bufB = bufA;
     // hand-over buffers: in the cluster form a level PUSHES its phi into the partner CTA's shared memory (remote
     // stores are fire-and-forget), so that the reads in the pointwise phase stay local
     cd *stash0 = CL ? cooperative_groups::this_cluster().map_shared_rank(bufA + BUF, 1 - lev) : bufA + BUF;
     const cd *stash0_other = CL ? bufA + BUF : sm + (1 - lev) * (BUF + 2 * N) + BUF;
-    cd *s_dv = sm + (PK ? 2 * BUF : C::NLEV_CTA * (BUF + 2 * N));
+    cd *s_dv = sm + (ILV ? 2 * BUF : C::NLEV_CTA * (BUF + 2 * N));
     double *s_xp = reinterpret_cast<double *>(s_dv + C::MAXCH);
     double *s_red = s_xp + C::MAXCH;              // 32 doubles of reduction scratch
     double *s_lc = s_red + 32;                    // local control: the run's state / constants ...
@@ -292,22 +321,27 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC>::NTHREADS, 1) grid_swe
     if (!PK && !valid) return;
     const int run = valid ? p.run_first + slot : p.run_first;
     auto level_sync = [&]() {                     // all threads of this thread's level (packed form: of the run)
-        if (PK) {
+        if (PKL) __syncwarp();
+        else if (PK) {
             if (RW == 1) __syncwarp(); else bar_sync(1 + rslot, C::RT);
         } else if (NAMED) bar_sync(1 + lev, TPL); else __syncthreads();
     };
+    // named barrier ids.  Plain form: 1,2 level-local transposes; 3..6 "phi of level n, order parity p is available".
+    // Packed form: interleaved layout one id per run (1 + rslot); level-per-warp layout five per run (four "available"
+    // ids and one for sums).  A "phi has been read" handshake is not needed: the buffers alternate with the order
+    // parity, and a level passes its wait for the partner's order j+1 only after the partner has finished order j.
+    const int bar_run = PKL ? 1 + 5 * rslot + 4 : 1 + rslot;
+    const int bar_full = PKL ? 1 + 5 * rslot : 3;
     auto both_sums = [&](double val, double &s0, double &s1) {
         if (CL) cluster_sums<C::NTHREADS>(val, s_red, tid, lev, s0, s1);
-        else if (PK) packed_sums<RW>(val, s_red, rtid, 1 + rslot, s0, s1);
+        else if (PKL) packed_level_sums<RW>(val, s_red, rtid, bar_run, s0, s1);
+        else if (PK) packed_sums<RW>(val, s_red, rtid, bar_run, s0, s1);
         else level_sums<C::NTHREADS, TPL>(val, s_red, tid, s0, s1);
     };
     const bool writer = (PK ? rtid == 0 && valid : tid == 0) && (!CL || lev == 0);   // the one thread that writes per-run scalars
     const int k1p = t / R3;       // k1' : which pass-1 output row this thread transforms in pass 2
     const int n3p = t % R3;       // n3' (also the lane's index c inside its group in pass 3)
-    // named barrier ids: 1,2 level-local transposes; 3..6 "phi of level n, order parity p is available";
-    // 7..10 "... has been read" (one pair per hand-over buffer, so arrive / sync alternate strictly on each id)
-    const int BAR_FULL_OWN = 3 + 2 * lev, BAR_FULL_OTH = 3 + 2 * (1 - lev), BAR_REL_OWN = 7 + 2 * lev,
-              BAR_REL_OTH = 7 + 2 * (1 - lev);
+    const int BAR_FULL_OWN = bar_full + 2 * lev, BAR_FULL_OTH = bar_full + 2 * (1 - lev);
 
     const long long prun = (long long)p.poly_stride * run;
     for (int i = rtid; i < p.nch; i += (PK ? C::RT : C::NTHREADS)) {
@@ -461,14 +495,13 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC>::NTHREADS, 1) grid_swe
             const int par = j & 1;
             cd *stash = stash0 + par * N;
             const cd *stash_other = stash0_other + par * N;
-            if (NAMED && j > 1) bar_sync(BAR_REL_OWN + par, C::NTHREADS);     // buffer `par` was last used two orders ago
-            if (!PK) {
+            if (!ILV) {
 #pragma unroll
                 for (int n1 = 0; n1 < 16; ++n1) stash[t + TPL * n1] = a[n1];
             }
 #pragma unroll
             for (int c4 = 0; c4 < 16; c4 += 4) tmem_store_c4(t_phi + c4 * 4, a + c4);
-            if (NAMED) bar_arrive(BAR_FULL_OWN + par, C::NTHREADS);   // producer side of a named barrier (no fence needed)
+            if (NAMED) bar_arrive(BAR_FULL_OWN + par, HN);   // producer side of a named barrier (no fence needed)
             // cluster form: one split-phase cluster barrier per order is the whole protocol -- the partner waits for
             // it before reading, and since the buffers alternate, this level's wait of order j+1 already implies
             // that the partner has finished reading buffer `par` of order j
@@ -498,7 +531,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC>::NTHREADS, 1) grid_swe
                 for (int q = 0; q < Q; ++q) dft<R3, false>(a + q * R3);
             }
             // k-space: kinetic multiplier (with c1 and the 1/N of the inverse transform folded in)
-            if (!PK) {
+            if (!ILV) {
 #pragma unroll
                 for (int e = 0; e < 16; ++e) a[e] = cscale(a[e], kc[e]);
             } else {
@@ -543,7 +576,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC>::NTHREADS, 1) grid_swe
             }
             // pointwise part (hamil_2d.py:60-71, phys_base.py:98-111) and accumulation (phys_base.py:170-172),
             // in chunks of four grid points: psi and own phi from TMEM, the other level's phi from shared memory
-            if (NAMED) bar_sync(BAR_FULL_OTH + par, C::NTHREADS);
+            if (NAMED) bar_sync(BAR_FULL_OTH + par, HN);
             if (CL) cl_wait();
             tmem_wait_st();
 #pragma unroll
@@ -552,7 +585,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC>::NTHREADS, 1) grid_swe
                 tmem_ld16(t_psi + c4 * 4, rp);
                 tmem_ld16(t_phi + c4 * 4, rs);
                 cd oth4[4], own4[4], acc4[4];
-                if (!PK) {
+                if (!ILV) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) oth4[i] = stash_other[t + TPL * (c4 + i)];
                 }
@@ -564,7 +597,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC>::NTHREADS, 1) grid_swe
                     const int n1 = c4 + i;
                     const double dd = dcoef[n1] - xpj;
                     cd r;
-                    if (PK) {                        // the coupling term is already inside a[]
+                    if (ILV) {                       // the coupling term is already inside a[]
                         r.x = fma(dd, own4[i].x, a[n1].x);
                         r.y = fma(dd, own4[i].y, a[n1].y);
                     } else {
@@ -580,9 +613,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC>::NTHREADS, 1) grid_swe
                 }
                 tmem_store_c4(t_psi + c4 * 4, acc4);
             }
-            if (NAMED) {
-                if (j + 2 <= last_j) bar_arrive(BAR_REL_OTH + par, C::NTHREADS);
-            } else if (!CL && !PK) {
+            if (!NAMED && !CL && !PK) {
                 __syncthreads();                                                   // (#3) hand-over buffer reuse
             }
         }
@@ -665,6 +696,8 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC>::NTHREADS, 1) grid_swe
             }
         } else if (!PK) {
             __syncthreads();
+        } else if (PKL) {
+            bar_sync(bar_run, C::RT);
         } else {
             level_sync();
         }
