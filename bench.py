@@ -152,6 +152,7 @@ def run_gpu_arm(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # One explicit stream for everything: the library launches on it and the timing events are recorded on it.
     # (torch's default stream has handle 0, which qc_create reads as "create your own stream": events recorded
