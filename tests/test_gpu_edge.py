@@ -23,13 +23,16 @@ def _rows(hist):
     return np.array([[r.it, r.goal_close, r.Fsm, r.E_int, r.J] for r in hist])
 
 
-def test_ragged_krotov_batch(ctx):
+@pytest.mark.parametrize("np_,pack", [(256, "0"), (256, "1"), (512, "1")])
+def test_ragged_krotov_batch(ctx, monkeypatch, np_, pack):
     """Three Krotov runs of different length (nt = 40, 64, 25) and amplitude in ONE plan: each must equal
-    the oracle run on its own (per-run nt, per-run interpolation table, padded trajectories)."""
+    the oracle run on its own (per-run nt, per-run interpolation table, padded trajectories) -- with one run per
+    CTA and in the packed form, where runs of different length share a CTA and the last CTA has empty run slots."""
     from qcontrol_b200 import control
+    monkeypatch.setenv("QC_GRID_PACK", pack)
     pbs = []
     for nt, scale in ((40, 1.0), (64, 0.7), (25, 1.3)):
-        user = conf_krotov(nt, 2, np_=256)
+        user = conf_krotov(nt, 2, np_=np_)
         user["fitter"]["propagation"]["E0"] *= scale
         pbs.append(qo.make_problem(user))
     gb = control.GridBatch(pbs, ctx=ctx)
@@ -201,4 +204,39 @@ def test_np4096_krotov_vs_oracle(ctx):
     for r, q in zip(hist[0], ref):
         assert np.allclose(r.E_tlist, q.E_tlist, rtol=1e-9, atol=1e-9 * np.abs(q.E_tlist).max())
     assert np.array_equal(_rows(hist[0]), _rows(hist[1]))
+    gb.close()
+
+
+@pytest.mark.parametrize("np_,batch", [(256, 700), (512, 650), (1024, 600)])
+def test_propagate_host_pipeline(ctx, np_, batch):
+    """qc_propagate_host (host buffers in, host buffers out; the call bench.py's e2e figure times): batches larger
+    than one pipeline chunk (592 runs) are cut into chunks over three streams -- at np <= 512 the full chunk runs
+    in the packed form and the tail with one run per CTA.  Result must equal the device-resident path
+    (set_state / sweep / get_state) and, for single runs, the oracle."""
+    from qcontrol_b200 import control, engine, synthetic
+    nt, nch = 6, 64
+    pbs = synthetic.krotov_batch(batch, np_, nt, nch, seed=77)
+    gb = control.GridBatch(pbs, ctx=ctx, store_traj=False)
+    pl = gb.plan
+    pl.set_E_base(gb._pad([gb._prescribed_field(p, control.FORWARD) for p in pbs]))
+    hin = np.ascontiguousarray(gb.psi0)
+    hout = np.zeros_like(hin)
+    pl.propagate_host(hin, hout, slot=0, l_first=1, nsteps=nt, renorm=True)
+    pl.set_state(hin)
+    pl.sweep(0, engine.FIELD_PRESCRIBED, 1, nt, True, -1, -1)
+    dev = pl.get_state()
+    assert np.abs(hout - dev).max() <= 1e-13          # packed / unpacked forms differ in the order of the norm sums
+    assert np.abs(hout - hin).max() > 1e-3            # it did propagate
+    for b in (0, 591, 592, batch - 1):
+        run = pbs[b]
+        pb = qo.Problem(task_type="trans_wo_control", hamil="ntriv", ntriv=1, np_=np_, nlevs=2, nb=1, L=run.L, T=run.T,
+                        dx=run.dx, x=run.x, v=run.v, vmin=run.vmin, akx2=run.akx2, psi0=run.psi0, psif=run.psif, m=run.m,
+                        nch=nch, nt=run.nt, E0=run.E0, t0=run.t0, sigma=run.sigma, nu_L=run.nu_L, nu=run.nu,
+                        envelope="gauss", carrier="exp", hf_hide=True, t_step=run.t_step, t_list=run.t_list)
+        st = qo.Stepper(pb, lambda s: pb.laser_field(pb.E0, s.t, pb.t0, pb.sigma), instrument=False)
+        st.start(pb.psi0[0], pb.psif[0], qo.FORWARD)
+        for _ in range(nt):
+            st.step(np.float64(0.0))
+        err = float(np.sqrt(run.dx * np.sum(np.abs(hout[b, 0] - st.psi) ** 2)))
+        assert err <= 1e-10 * nt, (np_, b, err)
     gb.close()
