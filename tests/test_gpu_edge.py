@@ -1,6 +1,5 @@
 """GPU edge cases the reference's domain has: ragged batches (runs of different length in one plan),
 unusual polynomial orders, the smallest / single-run batches, and the error behaviour of the C ABI."""
-import copy
 
 import numpy as np
 import pytest
