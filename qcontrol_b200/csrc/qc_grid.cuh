@@ -434,12 +434,12 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV>::NTHREADS, 1) gri
         cd eLx = cmk(1.0, 0.0);
         if (p.hf_hide && !start_only) {
             eLx = LOCAL ? cmk(s_ls[LS_XR], s_ls[LS_XI]) : p.expL[xrun + l];
-            const double den = eLx.x * eLx.x + eLx.y * eLx.y;
+            const double den = eLx.x * eLx.x + eLx.y * eLx.y, rden = 1.0 / den;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 if (lev == 0) {
                     cd n = cmulc(psi[i], eLx);
-                    psi[i] = cmk(n.x / den, n.y / den);
+                    psi[i] = cmk(div_rn_by(n.x, den, rden), div_rn_by(n.y, den, rden));
                 } else {
                     psi[i] = cmul(psi[i], eLx);
                 }
@@ -643,9 +643,9 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV>::NTHREADS, 1) gri
             }
             const double tot = fabs(n0 + n1s);
             if (p.renorm && tot > 0.0) {                     // propagation.py:430-433
-                const double s = sqrt(tot);
+                const double s = sqrt(tot), rs = 1.0 / s;       // x / s bit for bit, see div_rn_by
 #pragma unroll
-                for (int i = 0; i < 16; ++i) psi[i] = cmk(psi[i].x / s, psi[i].y / s);
+                for (int i = 0; i < 16; ++i) psi[i] = cmk(div_rn_by(psi[i].x, s, rs), div_rn_by(psi[i].y, s, rs));
             }
             // ---- record the rotating-frame state (fitter.py:301-309, 322-329) -----
             if (traj_out && lev == ov_lev) {
@@ -683,14 +683,14 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV>::NTHREADS, 1) gri
             }
             // ---- rotating frame out (propagation.py:440-441) ---------------------
             if (p.hf_hide) {
-                const double den = eLx.x * eLx.x + eLx.y * eLx.y;
+                const double den = eLx.x * eLx.x + eLx.y * eLx.y, rden = 1.0 / den;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     if (lev == 0) {
                         psi[i] = cmul(psi[i], eLx);
                     } else {
                         cd n = cmulc(psi[i], eLx);
-                        psi[i] = cmk(n.x / den, n.y / den);
+                        psi[i] = cmk(div_rn_by(n.x, den, rden), div_rn_by(n.y, den, rden));
                     }
                 }
             }

@@ -243,9 +243,9 @@ __global__ void __launch_bounds__(Grid2DCfg::NTHREADS, 1) grid2d_sweep_kernel(Gr
         }
         const double tot = fabs(whole * p.dxdy);
         if (p.renorm && tot > 0.0) {
-            const double s = sqrt(tot);
+            const double s = sqrt(tot), rs = 1.0 / s;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) a[i] = cmk(a[i].x / s, a[i].y / s);
+            for (int i = 0; i < 16; ++i) a[i] = cmk(div_rn_by(a[i].x, s, rs), div_rn_by(a[i].y, s, rs));
         }
         if (tix == 0 && tid == 0) p.norms[wave] = tot;
 #pragma unroll

@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(128) nlevel_sweep_kernel(NLevelParams p) {
     const double dx = p.dx[(long long)p.dx_stride * run];
     const double h_lambda = p.ctl[(long long)p.ctl_stride * run * 4 + 0];
     const int nt = (int)p.ctl[(long long)p.ctl_stride * run * 4 + 1];
+    const double inv_h_lambda = 1.0 / h_lambda;
     const double U = p.uwd ? p.uwd[(long long)p.uwd_stride * run * 3 + 0] : 0.0;
     const double W = p.uwd ? p.uwd[(long long)p.uwd_stride * run * 3 + 1] : 0.0;
     const double delta = p.uwd ? p.uwd[(long long)p.uwd_stride * run * 3 + 2] : 0.0;
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(128) nlevel_sweep_kernel(NLevelParams p) {
                 part.y += __shfl_xor_sync(0xffffffffu, part.y, o);
             }
             if (l <= nt) {
-                E = l > 0 ? cmk(cur.base.x - cur.s * part.y / h_lambda, cur.base.y) : cur.base;
+                E = l > 0 ? cmk(cur.base.x - div_rn_by(cur.s * part.y, h_lambda, inv_h_lambda), cur.base.y) : cur.base;
             } else {
                 E = cmk(0.0, 0.0);
             }
@@ -247,8 +248,9 @@ __global__ void __launch_bounds__(128) nlevel_sweep_kernel(NLevelParams p) {
         if (!p.single_step) {
             if (p.renorm && fabs(nsum) > 0.0) {
                 const double s = sqrt(fabs(nsum));
+                const double rs = 1.0 / s;
 #pragma unroll
-                for (int n = 0; n < NL; ++n) psi[n] = cmk(psi[n].x / s, psi[n].y / s);
+                for (int n = 0; n < NL; ++n) psi[n] = cmk(div_rn_by(psi[n].x, s, rs), div_rn_by(psi[n].y, s, rs));
             }
             if (l == nt || l == p.l_first + p.nsteps - 1) {
 #pragma unroll
