@@ -86,8 +86,8 @@ struct GridParams {
 // the only form for np = 4096 (a level alone fills the registers and shared memory of an SM) and the
 // low-latency form for batches too small to fill the GPU; the levels talk through distributed shared memory.
 // RPC > 0: the PACKED form for small grids -- RPC runs per CTA so that a CTA has four warps (all four tensor-memory
-// lane quadrants in use) and an SM holds eight; the two levels of a run are interleaved inside every warp (lanes L
-// and L^16), see the kernel.
+// lane quadrants in use) and an SM holds eight.  ILV: the two levels of a run are interleaved inside one warp (lanes
+// L and L^16; np = 256, where a level is half a warp); otherwise a level is one warp (np = 512), see the kernel.
 template <int LOG2N, bool CL = false, int RPC = 0, bool ILV = false>
 struct GridCfg {
     static constexpr int N = 1 << LOG2N;
@@ -294,9 +294,9 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV>::NTHREADS, 1) gri
     constexpr int RW = C::RT / 32;                // warps per run (packed form)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
-    // packed form: run slot rslot of this CTA, thread rtid of the run; the two levels of grid point set t sit in
-    // lanes L and L^16 of one warp, so the coupling term is a warp shuffle (in k space, where both levels hold the
-    // same frequencies) instead of a shared-memory hand-over, and a run synchronises on its own named barrier
+    // packed form: run slot rslot of this CTA, thread rtid of the run.  ILV: the two levels of grid point set t sit
+    // in lanes L and L^16 of one warp, so the coupling term is a warp shuffle (in k space, where both levels hold
+    // the same frequencies) instead of a shared-memory hand-over.  A run synchronises on named barriers of its own
     const int rslot = PK ? tid / C::RT : 0;
     const int rtid = PK ? tid - rslot * C::RT : tid;
     cd *sm = reinterpret_cast<cd *>(smem_raw + (PK ? rslot * C::RUN_BYTES : 0));
