@@ -191,3 +191,25 @@ def test_table_reporters_write_the_reference_formats(golden, tmp_path, flag):
     assert sorted(got) == sorted(want)
     for k in want:
         assert got[k] == want[k], k
+
+
+def test_shared_reciprocal_quotient_is_correctly_rounded():
+    """The kernels divide many values by one divisor (renormalisation psi / sqrt(norm), the rotating frame, the
+    field law / h_lambda) as rb = 1 / b once and  q = a rb,  r = fma(-q, b, a),  fma(r, rb, q)  per value
+    (div_rn_by in csrc/qc_fft.cuh).  This restates the three steps with exact rational arithmetic for the two
+    fused operations and checks that the result is the correctly rounded a / b the reference computes -- the
+    reason the change of r01k left every result bit-identical."""
+    from fractions import Fraction
+    rng = np.random.default_rng(2024)
+    n = 40000
+    a = rng.standard_normal(n) * 10.0 ** rng.integers(-30, 3, n)
+    b = np.concatenate([rng.uniform(0.5, 2.0, n // 2), 10.0 ** rng.uniform(-6, 3, n - n // 2)])
+    a[:10] = 0.0
+    bad = 0
+    for x, y in zip(a.tolist(), b.tolist()):
+        rb = 1.0 / y
+        q = x * rb
+        r = float(Fraction(x) - Fraction(q) * Fraction(y))          # fma(-q, y, x): one rounding
+        q2 = float(Fraction(q) + Fraction(r) * Fraction(rb))        # fma(r, rb, q): one rounding
+        bad += q2 != x / y
+    assert bad == 0
