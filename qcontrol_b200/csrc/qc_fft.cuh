@@ -27,7 +27,7 @@ __device__ __forceinline__ cd cscale(cd a, double s) { return cmk(a.x * s, a.y *
 __device__ __forceinline__ cd cfma(cd a, cd b, cd acc) {
     return cmk(fma(a.x, b.x, fma(-a.y, b.y, acc.x)), fma(a.x, b.y, fma(a.y, b.x, acc.y)));
 }
-// a / b, correctly rounded, from rb = RN(1 / b): q = RN(a rb), r = a - b q (exact in an FMA), RN(q + r rb) is the
+// a / b, correctly rounded, from rb = RN(1 / b): q = RN(a rb), r = a - b q (one FMA), RN(q + r rb) is the
 // correctly rounded quotient (Markstein 1990; the one exception, a significand of b of all ones, has probability
 // 2^-52).  Three dependent FMAs and no branch, against the ~15-instruction division routine with its slow-path
 // branch: where one divisor serves many dividends (renormalisation, rotating frame, the field law) the reference's
