@@ -1181,7 +1181,8 @@ extern "C" int32_t qc_propagate_host(qc_plan *pl, const qc_sweep_args *args, con
     qc_context *ctx = pl->ctx;
     cudaStream_t st = ctx->stream;
     const qc_plan_desc &d = pl->d;
-    int chunk = 592;                                         // 4 waves of 148 CTAs
+    // np = 2048: 4 waves of 148 CTAs; np = 256 in the packed form: one wave is 148 SMs x 2 CTAs x 4 runs
+    int chunk = pl->grid && pl->log2n == 8 ? 1184 : 592;
     if (const char *e = getenv("QC_E2E_CHUNK")) chunk = atoi(e) > 0 ? atoi(e) : chunk;
     if (!pl->grid || d.batch <= chunk || args->field_mode != QC_FIELD_PRESCRIBED) {
         QC_CUDA(cudaMemcpyAsync(pl->psi.p, psi_in, pl->state_elems * sizeof(cd), cudaMemcpyHostToDevice, st));

@@ -206,11 +206,11 @@ def test_np4096_krotov_vs_oracle(ctx):
     gb.close()
 
 
-@pytest.mark.parametrize("np_,batch", [(256, 700), (512, 650), (1024, 600)])
+@pytest.mark.parametrize("np_,batch", [(256, 1300), (512, 650), (1024, 600)])
 def test_propagate_host_pipeline(ctx, np_, batch):
     """qc_propagate_host (host buffers in, host buffers out; the call bench.py's e2e figure times): batches larger
-    than one pipeline chunk (592 runs) are cut into chunks over three streams -- at np <= 512 the full chunk runs
-    in the packed form and the tail with one run per CTA.  Result must equal the device-resident path
+    than one pipeline chunk (592 runs; 1184 at np = 256) are cut into chunks over three streams -- at np <= 512 the
+    full chunk runs in the packed form and the tail with one run per CTA.  Result must equal the device-resident path
     (set_state / sweep / get_state) and, for single runs, the oracle."""
     from qcontrol_b200 import control, engine, synthetic
     nt, nch = 6, 64
@@ -226,7 +226,7 @@ def test_propagate_host_pipeline(ctx, np_, batch):
     dev = pl.get_state()
     assert np.abs(hout - dev).max() <= 1e-13          # packed / unpacked forms differ in the order of the norm sums
     assert np.abs(hout - hin).max() > 1e-3            # it did propagate
-    for b in (0, 591, 592, batch - 1):
+    for b in (0, 591, 592, batch - 1) if np_ > 256 else (0, 1183, 1184, batch - 1):
         run = pbs[b]
         pb = qo.Problem(task_type="trans_wo_control", hamil="ntriv", ntriv=1, np_=np_, nlevs=2, nb=1, L=run.L, T=run.T,
                         dx=run.dx, x=run.x, v=run.v, vmin=run.vmin, akx2=run.akx2, psi0=run.psi0, psif=run.psif, m=run.m,
