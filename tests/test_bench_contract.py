@@ -1,0 +1,37 @@
+"""bench.py's reference arm (CPU only) against the JSON-line contract: one line on stdout, the keys the driver
+reads, `impl = reference`, a cpu_baseline describing the run; ranks other than 0 print nothing and exit 0."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(env_extra):
+    env = dict(os.environ)
+    env.update(env_extra)
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                           "--warmup", "0", "--cpu-steps", "2"], capture_output=True, text=True, env=env, timeout=600)
+
+
+def test_reference_arm_prints_one_json_line():
+    r = _run({"RANK": "0", "WORLD_SIZE": "2"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["steps"] == 1 and d["higher_is_better"] is True
+    assert d["metric"] == "wavefunction grid-pt*timesteps/s" and d["unit"] == "grid-pt*timesteps/s"
+    assert d["config"]["workload"] == "krotov_batch_8192x2048" and d["vs_baseline"] is None and d["dtype"] == "f64"
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_are_silent():
+    r = _run({"RANK": "1", "WORLD_SIZE": "2"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
