@@ -35,3 +35,27 @@ def test_reference_arm_prints_one_json_line():
 def test_reference_arm_other_ranks_are_silent():
     r = _run({"RANK": "1", "WORLD_SIZE": "2"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_gpu_arm_line_has_the_contract_keys():
+    """A small instance of the bench workload (296 runs x 4 steps) through bench.py itself: one JSON line with the
+    base contract's keys plus roofline / e2e / clocks / gpu_launches, all finite and positive."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--runs", "296", "--nt", "4", "--steps", "1",
+                        "--warmup", "3", "--no-cpu"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "e2e", "clocks", "gpu_launches", "cpu_baseline"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["value"] > 0 and d["gpu_launches"] > 0 and d["cpu_baseline"] is None
+    roof = d["roofline"]
+    assert roof["unit"] == "TFLOP/s" and 0.0 < roof["frac"] < 1.0 and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-12
+    e2e = d["e2e"]
+    assert e2e["value"] > 0 and e2e["h2d_bytes_per_step"] == e2e["d2h_bytes_per_step"] == 296 * 2 * 2048 * 16
+    assert d["clocks"]["sm_max_mhz"] and isinstance(d["clocks"]["reasons"], list)
