@@ -94,10 +94,16 @@ int32_t qc_timer_stop(qc_context *ctx, double *elapsed_ms); /* synchronises */
 int64_t qc_launch_count(qc_context *ctx);
 /* FP64 FMA throughput micro-benchmark on this device, TFLOP/s (roofline denominator) */
 int32_t qc_measure_fp64_peak(qc_context *ctx, double *tflops);
+/* free / total device memory of the context's GPU in bytes: the reference keeps every trajectory in host RAM
+ * (psi_tlist / chi_tlist, fitter.py:322-329); here they live in HBM, so batch entry points size their plans with
+ * this and qc_plan_footprint instead of failing with QC_ERR_NOMEM */
+int32_t qc_mem_info(qc_context *ctx, int64_t *free_bytes, int64_t *total_bytes);
 
 /* ---- plan ---------------------------------------------------------------- */
 int32_t qc_plan_create(qc_context *ctx, const qc_plan_desc *desc, qc_plan **out);
 int32_t qc_plan_destroy(qc_plan *plan);
+/* upper bound of the device bytes a plan of this shape allocates over its life (needs no GPU) */
+int32_t qc_plan_footprint(const qc_plan_desc *desc, int64_t *bytes);
 
 /* Potentials and kinetic multiplier: what Hamil2D*.__init__(v, akx2, np, U, W, delta, ntriv)
  * receives (hamil_2d.py:190-199).

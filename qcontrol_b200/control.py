@@ -25,6 +25,7 @@ import numpy as np
 
 from . import engine as eng
 from . import math_base
+from .functionals import F_batch, F_value as _F_value, a_batch, a_value as _a_value
 from .phys_consts import CM_TO_ERG, HZ_TO_CM, RED_PLANCK_H
 
 FORWARD, BACKWARD = 1, -1
@@ -41,41 +42,6 @@ class IterRow:
     E_int: float
     J: float
     E_tlist: np.ndarray
-
-
-def _F_value(kind, gc, nb):
-    """task_manager.py:162-207 on one run's goal-closeness vector."""
-    F = np.complex128(0)
-    if kind == "sm":
-        for a in range(nb):
-            for b in range(nb):
-                F -= gc[a] * gc[b].conjugate()
-    elif kind == "re":
-        for a in range(nb):
-            F -= gc[a].real
-    else:
-        for a in range(nb):
-            F -= gc[a] * gc[a].conjugate()
-    return F
-
-
-def _a_value(kind, psi_init, chi_init, dx):
-    """task_manager.py:209-268 (a_sm, a_re, a_ss) on one run."""
-    nb, nlevs, _ = psi_init.shape
-    a = np.zeros(nb, np.complex128)
-    if kind == "re":
-        a[:] = 0.5
-        return a
-    if kind == "sm":
-        for va in range(nb):
-            for v in range(nb):
-                for n in range(nlevs):
-                    a[va] += np.vdot(chi_init[v, n], psi_init[v, n]) * dx
-        return a
-    for v in range(nb):
-        for n in range(nlevs):
-            a[v] += np.vdot(chi_init[v, n], psi_init[v, n]) * dx
-    return a
 
 
 def energy_window(pb, direction=FORWARD, freq_mult=1.0):
@@ -187,10 +153,19 @@ def field_integral(Et, t_step):
     return np.complex128(np.sum(Et[1:] * np.conjugate(Et[1:])) * (t_step * 1e15))
 
 
+TRAJ_TASKS = ("optimal_control_krotov", "optimal_control_unit_transform")
+
+
 class _BatchBase:
-    def __init__(self, problems: Sequence, ctx: eng.Context = None, device: int = 0, store_traj=True):
+    def __init__(self, problems: Sequence, ctx: eng.Context = None, device: int = 0, store_traj=None):
+        """store_traj: allocate the two trajectory buffers [batch][nt_max+1][np] (grid) -- None = only for the task
+        types whose field update reads the previous opposite sweep (Krotov, unitary transformation); pass True to
+        record a prescribed-field sweep with ``propagate(record=True)``.  A filtering run of the shipped length
+        (nt = 800000, np = 2048) would otherwise allocate 2 x 26 GB it never touches."""
         self.pbs = list(problems)
         p0 = self.pbs[0]
+        if store_traj is None:
+            store_traj = getattr(p0, "task_type", "") in TRAJ_TASKS
         self.B = len(self.pbs)
         self.ctx = ctx or eng.Context(device)
         for p in self.pbs:
@@ -421,6 +396,8 @@ class GridBatch(_BatchBase):
         pl = self.plan
         hist: List[List[IterRow]] = [[] for _ in self.pbs]
         done = np.zeros(self.B, bool)
+        F_mid_1 = np.zeros(self.B)
+        self.errors = [""] * self.B
         sqrt_hf_T = np.array([np.complex128(cmath.sqrt(p.laser_field_hf(np.float64(1.0), p.T, p.pcos, p.w_list)))
                               for p in self.pbs])
         it = 0
@@ -444,22 +421,41 @@ class GridBatch(_BatchBase):
             for b, p in enumerate(self.pbs):
                 if done[b]:
                     continue
-                hist[b].append(rows[b])
-                reached = abs(rows[b].Fsm - p.F_goal) <= p.epsilon
                 limit = p.iter_max if iter_max is None else iter_max
-                if reached or (it >= limit and limit != -1):
-                    if not (reached and it == 0):
-                        pass
+                if it == 0 and abs(rows[b].Fsm - p.F_goal) <= p.epsilon:
+                    # goal met by the initial guess: the reference leaves the iteration before reporting it and
+                    # before the backward sweep (fitter.py:472-476), so the run has no row at all
+                    done[b] = True
+                    continue
+                hist[b].append(rows[b])
+                # The loop condition of time_propagation (fitter.py:545-546) is tested after the BACKWARD sweep of
+                # the iteration, which recomputes Fsm from a zeroed goal_close_vec (fitter.py:354-410): it sees
+                # F_type(0) = 0, not the forward value, so a Krotov run always uses its whole iteration budget
+                # unless |0 - F_goal| <= epsilon.  The divergence guard (fitter.py:550-560) sees the same zeros.
+                F_after = 0.0
+                if p.q and it >= 1:
+                    if it == p.iter_mid_1:
+                        F_mid_1[b] = F_after
+                    elif it == p.iter_mid_2:
+                        lim = -p.nb * p.nb * p.q
+                        if F_mid_1[b] > lim or F_after > lim or F_mid_1[b] < F_after:
+                            self.errors[b] = "The calculation is probably going to diverge.  Stopping the run..."
+                            done[b] = True
+                            continue
+                if abs(F_after - p.F_goal) <= p.epsilon or (it >= limit and limit != -1):
                     done[b] = True
                 else:
                     stop_all = False
-            # the reference always runs the backward sweep of an iteration it started, unless the goal
-            # was met in iteration 0 (fitter.py:472-476); results of that sweep only matter to the next one
-            if stop_all:
+            # the reference always runs the backward sweep of an iteration it started, unless the goal was met in
+            # iteration 0 (fitter.py:472-476); its results only matter to the next iteration -- and to the per-step
+            # tables of "iter_{k}b" when reporters are attached
+            if stop_all and (self.observer is None or not any(hist)):
                 break
             pl.krotov_terminal(1, sqrt_hf_T, 1)
             pl.snapshot_set(2)                            # chi(T): the "psi0" of the backward solver (fitter.py:247)
             self._sweep("iter_%db" % it, BACKWARD, (2, 0), 1, eng.FIELD_KROTOV_BWD, 1, self.nt_max, 0, 1)
+            if stop_all:
+                break
             it += 1
         return hist
 
@@ -596,13 +592,7 @@ class NLevelBatch(_BatchBase):
                 # reference's nested loops in the last bit
                 dyn = mode_dyn & (goal_close_abs != 0.0)
                 h_lambda = np.where(dyn, h0_all * nb_runs / np.sqrt(np.where(dyn, goal_close_abs, 1.0)), h0_all)
-                per_v = (np.conj(chi_init) * self.psi0).sum(axis=(2, 3)) * self.dx[:, None]     # [B][nb]
-                if kind == "sm":
-                    a0 = np.repeat(per_v.sum(axis=1, keepdims=True), per_v.shape[1], axis=1)
-                elif kind == "re":
-                    a0 = np.full_like(per_v, 0.5)
-                else:
-                    a0 = per_v
+                a0 = a_batch(kind, self.psi0, chi_init, self.dx)
             pl.set_control(h_lambda, self.nt.astype(np.float64), a0)
             if it == 0:
                 pl.set_E_base(self._pad(base_rows))
@@ -616,12 +606,7 @@ class NLevelBatch(_BatchBase):
                 # throughput mode: E_int reduced on the device, functional over the whole batch at once
                 E_int_all = pl.field_integral() * (t_steps * 1e15)
                 tau = gc.sum(axis=1)
-                if kind == "sm":
-                    F_all = -(tau * np.conj(tau)).real
-                elif kind == "re":
-                    F_all = -gc.real.sum(axis=1)
-                else:
-                    F_all = -(gc * np.conj(gc)).real.sum(axis=1)
+                F_all = F_batch(kind, gc)
             if not keep_fields:
                 active = ~done
                 J_all = F_all - h_lambda * h_lambda * E_int_all

@@ -211,6 +211,15 @@ __global__ void record_nlevel_kernel(const cd *psi, cd *traj_slice, int nb, int 
         traj_slice[(long long)n * nthreads + gt] = v < nb ? psi[((long long)run * nb + v) * nl + n] : qc::cmk(0.0, 0.0);
 }
 
+// out[run][x] = traj[run][index][x]: one recorded slice of a grid trajectory, contiguous for a single copy to the
+// host (the run stride (nt_max+1)*np*16 B of the buffer exceeds the 2 GiB pitch limit of a strided copy at the
+// shipped sizes: nt = 230000, np = 1024 -> 3.77 GB)
+__global__ void gather_grid_slice_kernel(const cd *traj, cd *out, long long run_stride, int np_) {
+    const cd *src = traj + run_stride * blockIdx.x;
+    cd *dst = out + (long long)np_ * blockIdx.x;
+    for (int i = threadIdx.x; i < np_; i += blockDim.x) dst[i] = src[i];
+}
+
 __global__ void gather_nlevel_kernel(const cd *traj_slice, cd *out, int nb, int nbp, int nl, long long nthreads) {
     const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gt >= nthreads) return;
@@ -465,6 +474,16 @@ extern "C" int32_t qc_timer_stop(qc_context *ctx, double *elapsed_ms) {
 
 extern "C" int64_t qc_launch_count(qc_context *ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int32_t qc_mem_info(qc_context *ctx, int64_t *free_bytes, int64_t *total_bytes) {
+    if (!ctx || !free_bytes || !total_bytes) return fail(QC_ERR_ARG, "qc_mem_info: NULL argument");
+    QC_CUDA(cudaSetDevice(ctx->device));
+    size_t f = 0, t = 0;
+    QC_CUDA(cudaMemGetInfo(&f, &t));
+    *free_bytes = (int64_t)f;
+    *total_bytes = (int64_t)t;
+    return QC_OK;
+}
+
 extern "C" int32_t qc_measure_fp64_peak(qc_context *ctx, double *tflops) {
     if (!ctx || !tflops) return fail(QC_ERR_ARG, "qc_measure_fp64_peak: NULL argument");
     QC_CUDA(cudaSetDevice(ctx->device));
@@ -569,6 +588,29 @@ extern "C" int32_t qc_plan_create(qc_context *ctx, const qc_plan_desc *desc, qc_
     }
     pl->ctl_batched = 0;
     *out = pl;
+    return QC_OK;
+}
+
+// Upper bound of the device memory a plan of this shape allocates over its life: state + four snapshots + four
+// instrumentation work buffers + one staging buffer, the per-step scalar tables, the two trajectory buffers, and
+// the per-run constants.  newcheb.run_variants sizes its sub-batches with it (qc_mem_info gives the free bytes).
+extern "C" int32_t qc_plan_footprint(const qc_plan_desc *desc, int64_t *bytes) {
+    if (!desc || !bytes) return fail(QC_ERR_ARG, "qc_plan_footprint: NULL argument");
+    const qc_plan_desc &d = *desc;
+    if (d.batch < 1 || d.nt_max < 1 || d.np < 1 || d.nlevs < 1 || d.nb < 1 || d.nch < 1)
+        return fail(QC_ERR_ARG, "qc_plan_footprint: non-positive size");
+    const bool grid = d.hamil == QC_HAMIL_NONTRIV;
+    int nbp = 1;
+    while (nbp < d.nb) nbp <<= 1;
+    const double state = (double)d.batch * d.nb * d.nlevs * d.np * sizeof(cd);
+    const double nt1 = (double)d.nt_max + 1.0;
+    double total = 10.0 * state;                                           // psi, snap[4], work[4], goal
+    total += (double)d.batch * nt1 * (5.0 * sizeof(cd) + sizeof(double));   // E_base, E_out, exp_L x 2, s_env, step times
+    if (d.store_traj)
+        total += 2.0 * sizeof(cd) * (grid ? (double)d.batch * nt1 * d.np : nt1 * d.nlevs * (double)d.batch * nbp);
+    total += (double)d.batch * ((double)d.nlevs * d.np * sizeof(double) + (double)d.nch * sizeof(cd) + 1024.0);
+    total += 1 << 20;
+    *bytes = (int64_t)total;
     return QC_OK;
 }
 
@@ -689,13 +731,16 @@ extern "C" int32_t qc_set_control(qc_plan *pl, const double *ctl, int32_t batche
 // ---------------------------------------------------------------------------
 // sweeps
 // ---------------------------------------------------------------------------
-template <int LOG2N, bool LOCAL = false, bool CL = false, int RPC = 0, bool ILV = false>
+#ifndef QC_GRID_VAR_DEFAULT
+#define QC_GRID_VAR_DEFAULT 1
+#endif
+template <int LOG2N, bool LOCAL = false, bool CL = false, int RPC = 0, bool ILV = false, int VAR = 0>
 static int32_t launch_grid(qc_plan *pl, const qc::GridParams &gp, cudaStream_t stream) {
-    typedef qc::GridCfg<LOG2N, CL, RPC, ILV> C;
+    typedef qc::GridCfg<LOG2N, CL, RPC, ILV, VAR> C;
     static bool attr_done[64] = {false};
     const int dev = pl->ctx->device;
     if (!attr_done[dev & 63]) {
-        QC_CUDA(cudaFuncSetAttribute(qc::grid_sweep_kernel<LOG2N, LOCAL, CL, RPC, ILV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        QC_CUDA(cudaFuncSetAttribute(qc::grid_sweep_kernel<LOG2N, LOCAL, CL, RPC, ILV, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)C::SMEM_BYTES));
         attr_done[dev & 63] = true;
     }
@@ -715,7 +760,7 @@ static int32_t launch_grid(qc_plan *pl, const qc::GridParams &gp, cudaStream_t s
         QC_CUDA(cudaLaunchKernelEx(&cfg, qc::grid_sweep_kernel<LOG2N, LOCAL, CL>, gp));
     } else {
         const int ctas = RPC > 0 ? (gp.run_count + RPC - 1) / RPC : gp.run_count;
-        qc::grid_sweep_kernel<LOG2N, LOCAL, CL, RPC, ILV><<<ctas, C::NTHREADS, C::SMEM_BYTES, stream>>>(gp);
+        qc::grid_sweep_kernel<LOG2N, LOCAL, CL, RPC, ILV, VAR><<<ctas, C::NTHREADS, C::SMEM_BYTES, stream>>>(gp);
     }
     pl->ctx->launches++;
     QC_CUDA(cudaGetLastError());
@@ -826,11 +871,16 @@ static int32_t run_sweep(qc_plan *pl, const qc_sweep_args *a, bool single_step, 
                 case 9: return launch_grid<9, false, false, 2, false>(pl, g, lst);
             }
         }
+        // kernel variants of the plain form (qc_grid.cuh, GridCfg::VAR); QC_GRID_VAR overrides the default (A/B runs)
+        int var = QC_GRID_VAR_DEFAULT;
+        if (const char *e = getenv("QC_GRID_VAR")) var = atoi(e);
         switch (pl->log2n) {
             case 8: return launch_grid<8>(pl, g, lst);
             case 9: return launch_grid<9>(pl, g, lst);
             case 10: return launch_grid<10>(pl, g, lst);
-            case 11: return launch_grid<11>(pl, g, lst);
+            case 11:
+                if (var == 1) return launch_grid<11, false, false, 0, false, 1>(pl, g, lst);
+                return launch_grid<11>(pl, g, lst);
         }
         return fail(QC_ERR_ARG, "qc_sweep: unsupported np");
     }
@@ -1137,9 +1187,13 @@ extern "C" int32_t qc_get_traj(qc_plan *pl, int32_t buffer, int32_t index, doubl
     const qc_plan_desc &d = pl->d;
     cudaStream_t st = pl->ctx->stream;
     if (pl->grid) {
-        QC_CUDA(cudaMemcpy2DAsync(out, (size_t)d.np * sizeof(cd), pl->traj[buffer].p + (size_t)index * d.np,
-                                  (size_t)(d.nt_max + 1) * d.np * sizeof(cd), (size_t)d.np * sizeof(cd), d.batch,
-                                  cudaMemcpyDeviceToHost, st));
+        const size_t n = (size_t)d.batch * d.np;
+        if (pl->goal.n < n) QC_CUDA(pl->goal.alloc(n));
+        gather_grid_slice_kernel<<<d.batch, 256, 0, st>>>(pl->traj[buffer].p + (size_t)index * d.np, pl->goal.p,
+                                                          (long long)(d.nt_max + 1) * d.np, d.np);
+        pl->ctx->launches++;
+        QC_CUDA(cudaGetLastError());
+        QC_CUDA(cudaMemcpyAsync(out, pl->goal.p, n * sizeof(cd), cudaMemcpyDeviceToHost, st));
     } else {
         const size_t n = (size_t)d.batch * d.nb * d.nlevs;
         if (pl->goal.n < n) QC_CUDA(pl->goal.alloc(n));

@@ -88,7 +88,14 @@ struct GridParams {
 // RPC > 0: the PACKED form for small grids -- RPC runs per CTA so that a CTA has four warps (all four tensor-memory
 // lane quadrants in use) and an SM holds eight.  ILV: the two levels of a run are interleaved inside one warp (lanes
 // L and L^16; np = 256, where a level is half a warp); otherwise a level is one warp (np = 512), see the kernel.
-template <int LOG2N, bool CL = false, int RPC = 0, bool ILV = false>
+// VAR (plain one-run-per-CTA form at np = 2048 only) selects kernel variants that are compared on the GPU by
+// tools/variant_compare.py:  bit 0 (TMH) = the phi hand-over between the two levels goes through TENSOR MEMORY instead
+// of shared memory.  Thread t of level 0 (warp w) and thread t of level 1 (warp w + 4) sit on the same tensor-memory
+// lane, so (a) they can share ONE copy of each twiddle table, which frees 128 of the pair's 512 columns, and (b) the
+// freed columns hold the second phi buffer of each level, so the partner reads this level's phi of either order parity
+// straight from the lane with tcgen05.ld.  Shared memory then carries nothing but the four FFT transposes per order:
+// 10 -> 8 complex128 accesses per point and order (-20 % of the busiest pipe), 200 KB -> 68 KB per CTA.
+template <int LOG2N, bool CL = false, int RPC = 0, bool ILV = false, int VAR = 0>
 struct GridCfg {
     static constexpr int N = 1 << LOG2N;
     static constexpr int TPL = N / 16;          // threads per level
@@ -102,6 +109,8 @@ struct GridCfg {
     static constexpr int NTHREADS = PK ? RPC * RT : NLEV_CTA * TPL;
     static constexpr int MAXCH = 128;
     static constexpr bool NAMED = !CL && !PK && TPL >= 32;   // a level is made of whole warps: per-level named barriers
+    static constexpr bool TMH = (VAR & 1) != 0;              // phi hand-over through tensor memory
+    static_assert(!TMH || (!CL && !PK && TPL == 128), "tensor-memory hand-over: levels must be warps w and w + 4");
     static constexpr int TM_COLS = NTHREADS > 128 ? 512 : 256;   // 256 TMEM columns per warp slot
     // shared memory (complex elements): per level ONE transpose buffer (forward and inverse passes use it in turn:
     // every element is either private to an R3-lane group or read by the thread that wrote it, except across the two
@@ -109,11 +118,11 @@ struct GridCfg {
     // then dv, xp and 32 doubles of reduction scratch (the last one carries the TMEM base address)
     // packed form: per run two transpose buffers (level-per-warp layout: and the four hand-over buffers), dv, xp and
     // 16 doubles of reduction scratch; then 32 doubles per CTA
-    static constexpr int LEVEL_ELEMS = ILV ? BUF : BUF + 2 * N;     // complex elements of shared memory per level
+    static constexpr int LEVEL_ELEMS = (ILV || TMH) ? BUF : BUF + 2 * N;     // complex elements of shared memory per level
     static constexpr size_t RUN_BYTES = sizeof(cd) * (size_t)(2 * LEVEL_ELEMS + MAXCH) + sizeof(double) * (size_t)(MAXCH + 16);
     static constexpr size_t SMEM_BYTES =
         PK ? RPC * RUN_BYTES + sizeof(double) * 32
-           : sizeof(cd) * (size_t)(NLEV_CTA * (BUF + 2 * N)) + sizeof(double) * (size_t)(3 * MAXCH + 32 + LC_STRIDE + LS_COUNT);
+           : sizeof(cd) * (size_t)(NLEV_CTA * LEVEL_ELEMS) + sizeof(double) * (size_t)(3 * MAXCH + 32 + LC_STRIDE + LS_COUNT);
 };
 
 // skewed position of element (k2, n3) inside a lane group's private 16*R3 region
@@ -279,13 +288,15 @@ __device__ __forceinline__ void cluster_sums(double val, double *s_red, int tid,
     sum1 = lev == 0 ? oth : own;
 }
 
-template <int LOG2N, bool LOCAL = false, bool CL = false, int RPC = 0, bool ILV = false>
-__global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV>::NTHREADS, 1) grid_sweep_kernel(GridParams p) {
+template <int LOG2N, bool LOCAL = false, bool CL = false, int RPC = 0, bool ILV = false, int VAR = 0>
+__global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1) grid_sweep_kernel(GridParams p) {
     static_assert(!(LOCAL && CL), "local control runs in the single-CTA form");
     static_assert(!(RPC > 0 && (LOCAL || CL)), "the packed form exists for the plain single-CTA kernel only");
     static_assert(!ILV || RPC > 0, "interleaved levels are a layout of the packed form");
     static_assert(ILV || RPC == 0 || GridCfg<LOG2N>::TPL == 32, "packed level-per-warp layout: a level is one warp");
-    typedef GridCfg<LOG2N, CL, RPC, ILV> C;
+    typedef GridCfg<LOG2N, CL, RPC, ILV, VAR> C;
+    static_assert(!(C::TMH && LOCAL), "local control keeps the shared-memory hand-over (it reuses the buffers)");
+    constexpr bool TMH = C::TMH;
     constexpr int N = C::N, TPL = C::TPL, R3 = C::R3, Q = C::Q, S1 = C::S1, BUF = C::BUF;
     constexpr bool PK = C::PK;
     constexpr bool PKL = PK && !ILV;              // packed, a level per warp: shared-memory hand-over like the plain form
@@ -302,13 +313,13 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV>::NTHREADS, 1) gri
     cd *sm = reinterpret_cast<cd *>(smem_raw + (PK ? rslot * C::RUN_BYTES : 0));
     const int lev = CL ? (int)cooperative_groups::this_cluster().block_rank() : ILV ? (rtid >> 4) & 1 : rtid / TPL;
     const int t = CL ? tid : ILV ? (rtid & 15) | ((rtid >> 5) << 4) : rtid - lev * TPL;
-    cd *bufA = sm + (CL ? 0 : lev) * (ILV ? BUF : BUF + 2 * N);
+    cd *bufA = sm + (CL ? 0 : lev) * C::LEVEL_ELEMS;
     cd *bufB = bufA;
     // hand-over buffers: in the cluster form a level PUSHES its phi into the partner CTA's shared memory (remote
     // stores are fire-and-forget), so that the reads in the pointwise phase stay local
     cd *stash0 = CL ? cooperative_groups::this_cluster().map_shared_rank(bufA + BUF, 1 - lev) : bufA + BUF;
-    const cd *stash0_other = CL ? bufA + BUF : sm + (1 - lev) * (BUF + 2 * N) + BUF;
-    cd *s_dv = sm + (ILV ? 2 * BUF : C::NLEV_CTA * (BUF + 2 * N));
+    const cd *stash0_other = CL ? bufA + BUF : sm + (1 - lev) * C::LEVEL_ELEMS + BUF;
+    cd *s_dv = sm + (ILV ? 2 * BUF : C::NLEV_CTA * C::LEVEL_ELEMS);
     double *s_xp = reinterpret_cast<double *>(s_dv + C::MAXCH);
     double *s_red = s_xp + C::MAXCH;              // 32 doubles of reduction scratch
     double *s_lc = s_red + 32;                    // local control: the run's state / constants ...
@@ -397,13 +408,23 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV>::NTHREADS, 1) gri
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *s_tmem;
     const int warp = tid >> 5;
-    const uint32_t t_psi = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 256);
-    const uint32_t t_phi = t_psi + 64;
-    const uint32_t t_tw1 = t_psi + 128, t_tw2 = t_psi + 192;
-    tmem_fill_twiddles(t_tw1, p.tw1[S1 + t]);        // w_N^t          (host-computed root, forward value)
-    tmem_fill_twiddles(t_tw2, p.tw2[R3 + n3p]);      // w_{16 R3}^{n3'}
-    tmem_wait_st();
+    // plain layout: 256 private columns per warp slot: psi, own phi, the two twiddle tables.
+    // TMH layout: the 512 columns of a lane are shared by thread t of level 0 (warp w) and of level 1 (warp w + 4):
+    // [0,128) psi of level 0 / 1, [128,256) ONE copy of the two twiddle tables (same t, same tables), [256,512) phi of
+    // level 0 / 1 for even / odd polynomial orders -- the partner reads them in place
+    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t t_psi = TMH ? t_lane + (uint32_t)(lev * 64) : t_lane + (uint32_t)((warp >> 2) * 256);
+    const uint32_t t_phi = TMH ? t_lane + 256 + (uint32_t)(lev * 128) : t_psi + 64;
+    const uint32_t t_phi_oth = t_lane + 256 + (uint32_t)((1 - lev) * 128);          // TMH only
+    const uint32_t t_tw1 = TMH ? t_lane + 128 : t_psi + 128, t_tw2 = t_tw1 + 64;
+    if (!TMH || lev == 0) {
+        tmem_fill_twiddles(t_tw1, p.tw1[S1 + t]);        // w_N^t          (host-computed root, forward value)
+        tmem_fill_twiddles(t_tw2, p.tw2[R3 + n3p]);      // w_{16 R3}^{n3'}
+        tmem_wait_st();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     const cd *traj_in = p.traj_in ? p.traj_in + (long long)run * (p.nt_max + 1) * N : nullptr;
     cd *traj_out = p.traj_out ? p.traj_out + (long long)run * (p.nt_max + 1) * N : nullptr;
@@ -495,13 +516,14 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV>::NTHREADS, 1) gri
             const int par = j & 1;
             cd *stash = stash0 + par * N;
             const cd *stash_other = stash0_other + par * N;
-            if (!ILV) {
+            if (!ILV && !TMH) {
 #pragma unroll
                 for (int n1 = 0; n1 < 16; ++n1) stash[t + TPL * n1] = a[n1];
             }
+            const uint32_t t_phi_j = TMH ? t_phi + (uint32_t)(par * 64) : t_phi;
 #pragma unroll
-            for (int c4 = 0; c4 < 16; c4 += 4) tmem_store_c4(t_phi + c4 * 4, a + c4);
-            if (NAMED) bar_arrive(BAR_FULL_OWN + par, HN);   // producer side of a named barrier (no fence needed)
+            for (int c4 = 0; c4 < 16; c4 += 4) tmem_store_c4(t_phi_j + c4 * 4, a + c4);
+            if (NAMED && !TMH) bar_arrive(BAR_FULL_OWN + par, HN);   // producer side of a named barrier (no fence needed)
             // cluster form: one split-phase cluster barrier per order is the whole protocol -- the partner waits for
             // it before reading, and since the buffers alternate, this level's wait of order j+1 already implies
             // that the partner has finished reading buffer `par` of order j
@@ -510,6 +532,13 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV>::NTHREADS, 1) gri
             {
                 TmemTwiddles tw(t_tw1);
                 dft16_table_out<false>(a, tw, [&](int k1, cd val) { bufA[k1 * S1 + t] = val; });
+            }
+            if (TMH) {
+                // hand-over through tensor memory: the asynchronous stores of phi have long landed behind the
+                // butterflies of pass 1; make them visible to the partner warp and signal "phi of this parity is there"
+                tmem_wait_st();
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                bar_arrive(BAR_FULL_OWN + par, HN);
             }
             level_sync();                                                           // (#1)
 #pragma unroll
@@ -577,21 +606,24 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV>::NTHREADS, 1) gri
             // pointwise part (hamil_2d.py:60-71, phys_base.py:98-111) and accumulation (phys_base.py:170-172),
             // in chunks of four grid points: psi and own phi from TMEM, the other level's phi from shared memory
             if (NAMED) bar_sync(BAR_FULL_OTH + par, HN);
+            if (TMH) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (CL) cl_wait();
             tmem_wait_st();
 #pragma unroll
             for (int c4 = 0; c4 < 16; c4 += 4) {
-                uint32_t rp[16], rs[16];
+                uint32_t rp[16], rs[16], ro[16];
                 tmem_ld16(t_psi + c4 * 4, rp);
-                tmem_ld16(t_phi + c4 * 4, rs);
+                tmem_ld16(t_phi_j + c4 * 4, rs);
+                if (TMH) tmem_ld16(t_phi_oth + (uint32_t)(par * 64) + c4 * 4, ro);
                 cd oth4[4], own4[4], acc4[4];
-                if (!ILV) {
+                if (!ILV && !TMH) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) oth4[i] = stash_other[t + TPL * (c4 + i)];
                 }
                 tmem_wait_ld();
                 tmem_unpack_c4(rp, acc4);
                 tmem_unpack_c4(rs, own4);
+                if (TMH) tmem_unpack_c4(ro, oth4);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int n1 = c4 + i;

@@ -76,10 +76,25 @@ class Context:
     def launches(self) -> int:
         return int(lib.qc_launch_count(self._h))
 
+    def mem_info(self):
+        """(free, total) bytes of the device's memory."""
+        f, t = C.c_int64(), C.c_int64()
+        check(lib.qc_mem_info(self._h, C.byref(f), C.byref(t)))
+        return int(f.value), int(t.value)
+
     def fp64_peak_tflops(self) -> float:
         tf = C.c_double()
         check(lib.qc_measure_fp64_peak(self._h, C.byref(tf)))
         return tf.value
+
+
+def plan_footprint(hamil, np_, nlevs, nb, nch, batch, nt_max, hf_hide=False, store_traj=False) -> int:
+    """Upper bound of the device bytes a plan of this shape allocates over its life (qc_plan_footprint)."""
+    d = PlanDesc(int(hamil), int(np_), int(nlevs), int(nb), int(nch), int(batch), int(nt_max), int(bool(hf_hide)),
+                 int(bool(store_traj)), 0)
+    out = C.c_int64()
+    check(lib.qc_plan_footprint(C.byref(d), C.byref(out)))
+    return int(out.value)
 
 
 class Plan:

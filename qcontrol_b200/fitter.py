@@ -22,7 +22,7 @@ from types import SimpleNamespace
 
 import numpy
 
-from . import control, engine as _eng, math_base, phys_base
+from . import control, engine as _eng, functionals, math_base, phys_base
 from .config import TaskRootConfiguration
 from .phys_base import ExpectationValues, SigmaExpectationValues
 from .propagation import PropagationSolver
@@ -54,11 +54,17 @@ class FitterReporter:
 
 
 def report_stride(rep) -> int:
-    """How often a propagation reporter keeps a time point.  The reference calls reporters every step
-    and lets them filter on ``l % mod == 0`` (reporter.py:110-164, tests/test_tools.py:189-194); reading
-    that modulus lets the GPU path synchronise only on the steps that are actually recorded."""
-    if hasattr(rep, "reps"):          # MultiplePropagationReporter: the finest of its members, none = never
-        return min([report_stride(r) for r in rep.reps], default=1 << 30)
+    """The steps at which a propagation reporter must be called.  The reference calls every reporter at every step
+    and lets each filter on ``l % mod == 0`` (reporter.py:110-164, tests/test_tools.py:189-194); the GPU path
+    synchronises only on multiples of the returned stride.  For a fan-out reporter this is the GREATEST COMMON
+    DIVISOR of its members' moduli -- every member still filters on its own modulus, so no record any of them would
+    keep is skipped (the minimum would lose step 100 for members with moduli 100 and 30).  0 = no member ever
+    keeps a step."""
+    if hasattr(rep, "reps"):          # MultiplePropagationReporter
+        g = 0
+        for r in rep.reps:
+            g = math.gcd(g, report_stride(r))
+        return g
     for holder in (rep, getattr(rep, "conf", None), getattr(rep, "_conf", None)):
         if holder is None:
             continue
@@ -100,7 +106,11 @@ class BatchObserver:
                     per_run.append(r)
                 self._reps.append(per_run)
             self._open_id = prop_id
-            batch.stride = min(report_stride(r) for per_run in self._reps for r in per_run)
+            g = 0
+            for per_run in self._reps:
+                for r in per_run:
+                    g = math.gcd(g, report_stride(r))
+            batch.stride = g if g > 0 else 1 << 30
         fields = pl.get_fields() if l > 0 else None
         E_all, fm_all, Efull = [], [], numpy.zeros(batch.B, numpy.complex128)
         for b, pb in enumerate(batch.pbs):
@@ -191,14 +201,8 @@ class FittingSolver:
 
     # ------------------------------------------------------------------------------------------
     def _functional_kind(self):
-        probe = numpy.array([1.0 + 2.0j] * self.basis_length)
-        val = self.F_type(probe, self.basis_length)
-        nb = self.basis_length
-        if abs(val + nb * nb * 5.0) < 1e-9:
-            return "sm"
-        if abs(val + nb * 1.0) < 1e-9:
-            return "re"
-        return "ss"
+        """"sm" / "re" / "ss": which functional the F_type callable is (task_manager.py:162-207)."""
+        return functionals.kind_of(self.F_type)
 
     def _carrier(self):
         """("exp", nu) when the high-frequency callable is exp(i 2 pi nu freq_mult t) (task_manager.py:73-86),
@@ -253,6 +257,9 @@ class FittingSolver:
         try:
             if pb.task_type == "optimal_control_krotov":
                 hist = batch.run_krotov()
+                if batch.errors[0]:                      # divergence guard (fitter.py:550-560)
+                    self._emit(hist[0], t_list, pb)
+                    raise ValueError(batch.errors[0])
             elif pb.task_type == "optimal_control_unit_transform":
                 hist = batch.run_unit_transform()
                 if batch.errors[0]:

@@ -136,13 +136,56 @@ def write_tables(out_path, rows, t_list, nt, imin=-1):
                 g.write("{:2d} {:.6f} {:.6e}\n".format(r.it, t_list[i] * 1e+15, abs(r.E_tlist[i])))
 
 
-def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True):
-    """Expand -> configure -> shard -> batched GPU runs -> per-run tables.  Returns {run index: rows}."""
+def memory_chunks(confs, idxs, free_bytes, fraction=0.8):
+    """Split the runs ``idxs`` of one plan shape into sub-batches whose plans fit the free device memory.
+
+    The reference keeps psi_tlist / chi_tlist in host RAM, one run per job (fitter.py:322-329); here the two
+    trajectory buffers of a Krotov / UT plan live in HBM: 2 * (nt + 1) * np * 16 B per run on the grid (7.5 GB for
+    the shipped Krotov input), so one plan per shape group does not fit arbitrary batches.  Runs are taken longest
+    first, so that a sub-batch holds runs of similar length (the plan is sized by its longest run), and a sub-batch
+    is closed when qc_plan_footprint of one more run would exceed ``fraction`` of the free bytes."""
+    if not idxs:
+        return []
+    c0 = confs[idxs[0]]
+    grid = c0.hamil_type == TaskRootConfiguration.HamilType.NTRIV
+    hamil = _eng.HAMIL_NONTRIV if grid else _eng.HAMIL_BH_X
+    traj = _NAMES.get(c0.task_type) in control.TRAJ_TASKS
+    cap = fraction * free_bytes
+
+    def fits(n, nt_max):
+        return _eng.plan_footprint(hamil, c0.np, c0.nlevs, c0.nb, c0.fitter.propagation.nch, n, nt_max,
+                                   bool(c0.fitter.hf_hide) and grid, traj) <= cap
+
+    order = sorted(idxs, key=lambda i: (-int(confs[i].fitter.propagation.nt), i))
+    chunks, cur = [], []
+    for i in order:
+        nt_max = int(confs[(cur or [i])[0]].fitter.propagation.nt)
+        if cur and not fits(len(cur) + 1, nt_max):
+            chunks.append(sorted(cur))
+            cur = []
+            nt_max = int(confs[i].fitter.propagation.nt)
+        if not cur and not fits(1, nt_max):
+            raise MemoryError("run #%d alone (nt = %d, np = %d) needs more than %.0f%% of the free device memory (%.1f GB)"
+                              % (i, nt_max, c0.np, 100 * fraction, free_bytes / 1e9))
+        cur.append(i)
+    if cur:
+        chunks.append(sorted(cur))
+    return chunks
+
+
+def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True, timings=None):
+    """Expand -> configure -> shard -> batched GPU runs -> per-run tables.  Returns {run index: rows}.
+    ``timings`` (a dict, optional) receives the wall-clock split of this rank: configuration, per-run task set-up
+    (task_manager.create + report set-up), plan set-up (tables of step scalars, Newton tables, uploads), the control
+    loops themselves, and reporting."""
     import contextlib
     import io
+    import time
+    tm_ = {"config_s": 0.0, "task_setup_s": 0.0, "plan_setup_s": 0.0, "run_s": 0.0, "report_s": 0.0, "plans": 0}
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0")) if device is None else device
+    t_mark = time.perf_counter()
     confs, costs, shapes = [], [], []
     for i, data_task in enumerate(variants):
         with contextlib.redirect_stdout(io.StringIO()):
@@ -158,7 +201,15 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True):
     results = {}
     ctx = _eng.Context(local)
     OT = ReportRootConfiguration.ReportFitterConfiguration.OutputType
-    for shape, idxs in qbatch.plan_groups(shapes, mine).items():
+    tm_["config_s"] = time.perf_counter() - t_mark
+    work = []
+    for shape, group in qbatch.plan_groups(shapes, mine).items():
+        try:
+            work += memory_chunks(confs, group, ctx.mem_info()[0])
+        except MemoryError as e:
+            print("An exception interrupted the jobs %s: %s" % (group, e), file=sys.stderr)
+    for idxs in work:
+        t_mark = time.perf_counter()
         pbs, reps = [], []
         for i in idxs:
             with contextlib.redirect_stdout(io.StringIO()):
@@ -170,8 +221,13 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True):
             print_input(ct.fitter.out_path, confs[i], "table_inp_-1.txt")
             reps.append(reporter.MultipleFitterReporter(ct.fitter, cp.fitter).open())
             pbs.append(problem_from(confs[i], tm))
+        tm_["task_setup_s"] += time.perf_counter() - t_mark
+        t_mark = time.perf_counter()
         grid = pbs[0].hamil == "ntriv"
         b = (control.GridBatch if grid else control.NLevelBatch)(pbs, ctx=ctx)
+        tm_["plan_setup_s"] += time.perf_counter() - t_mark
+        tm_["plans"] += 1
+        t_mark = time.perf_counter()
         if any(r.conf_rep_table.plotting_flag in (OT.ALL, OT.TABLES) for r in reps):
             # per-step tables were asked for: instrument the resident states at the steps the tables keep
             from .fitter import BatchObserver
@@ -194,6 +250,9 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True):
         else:
             hist = b.run_prescribed()
         errors = getattr(b, "errors", [""] * len(idxs))
+        ctx.synchronize()
+        tm_["run_s"] += time.perf_counter() - t_mark
+        t_mark = time.perf_counter()
         if b.observer is not None:
             b.observer.close()
         for k, i in enumerate(idxs):
@@ -208,7 +267,10 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True):
             elif verbose:
                 print("Job #%d is done" % i)
         b.close()
+        tm_["report_s"] += time.perf_counter() - t_mark
     ctx.close()
+    if timings is not None:
+        timings.update(tm_)
     return results
 
 

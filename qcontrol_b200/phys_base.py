@@ -13,6 +13,7 @@ This is the slow, call-by-call compatibility path; the batched sweeps live in co
 from __future__ import annotations
 
 import cmath
+import threading
 
 import numpy
 
@@ -44,14 +45,25 @@ class SigmaExpectationValues:
 
 
 # ----------------------------------------------------------------------------- plan cache
-_CTX = {}
-_SESSIONS = {}
+# The reference farms its jobs over a thread pool (newcheb.py:656-659), so this layer must be callable from several
+# host threads at once.  Every thread gets its OWN context (device binding + stream) and its own session cache:
+# nothing mutable is shared between threads, calls of different threads run concurrently on different streams
+# (ctypes releases the GIL), and the sequences upload -> step -> download of two threads can never interleave on
+# one plan.  The contexts of a thread are released when the thread ends.
+_TLS = threading.local()
+
+
+def _tls():
+    if not hasattr(_TLS, "ctx"):
+        _TLS.ctx, _TLS.sessions = {}, {}
+    return _TLS
 
 
 def default_context(device: int = 0) -> _eng.Context:
-    if device not in _CTX:
-        _CTX[device] = _eng.Context(device)
-    return _CTX[device]
+    ctxs = _tls().ctx
+    if device not in ctxs:
+        ctxs[device] = _eng.Context(device)
+    return ctxs[device]
 
 
 class Session:
@@ -90,15 +102,16 @@ class Session:
 
 
 def session_for(hamil2D, nlevs, nch, dx=1.0) -> Session:
+    sessions = _tls().sessions
     key = (id(hamil2D), int(nlevs), int(nch), float(dx))
-    s = _SESSIONS.get(key)
+    s = sessions.get(key)
     if s is None or s.h is not hamil2D:
-        if len(_SESSIONS) > 32:
-            for old in list(_SESSIONS.values()):
+        if len(sessions) > 32:
+            for old in list(sessions.values()):
                 old.plan.close()
-            _SESSIONS.clear()
+            sessions.clear()
         s = Session(hamil2D, nlevs, nch, dx=dx)
-        _SESSIONS[key] = s
+        sessions[key] = s
     return s
 
 

@@ -13,6 +13,7 @@ The HTML plot reporters (reporter.py:167-530, 635-788) are presentation only and
 from __future__ import annotations
 
 import copy
+import math
 import os
 
 from .config import ReportRootConfiguration
@@ -88,8 +89,11 @@ class MultiplePropagationReporter(PropagationReporter):
             self.reps.append(TablePropagationReporter(os.path.join(out_path, "tables"), nlvls, conf_rep_table))
 
     @property
-    def mod_fileout(self):          # lets the GPU path synchronise only on the steps that are written
-        return min([r.conf.mod_fileout for r in self.reps], default=1 << 30)
+    def mod_fileout(self):          # lets the GPU path synchronise only on steps some member writes: gcd of the moduli
+        g = 0
+        for r in self.reps:
+            g = math.gcd(g, int(r.conf.mod_fileout))
+        return g if g > 0 else 1 << 30
 
     def open(self):
         for r in self.reps:

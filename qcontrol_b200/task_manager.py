@@ -16,7 +16,7 @@ import math
 
 import numpy
 
-from . import grid_setup, hamil_2d, math_base
+from . import functionals, grid_setup, hamil_2d, math_base
 from .config import TaskRootConfiguration
 from .phys_consts import DALT_TO_AU, HART_TO_CM
 from .psi_basis import Psi, PsiBasis
@@ -96,51 +96,30 @@ class _LaserFieldsHighFrequencyPart:
 
 
 # ----------------------------------------------------------------------------- functionals (task_manager.py:162-268)
+def _tagged(kind, fn):
+    fn.kind = kind
+    return staticmethod(fn)
+
+
 class _F_type:
-    @staticmethod
-    def F_sm(gc_vec, nb):
-        F = numpy.complex128(0)
-        for a in range(nb):
-            for b in range(nb):
-                F -= gc_vec[a] * gc_vec[b].conjugate()
-        return F
+    """F_type(gc_vec, nb) callables with the reference's names; the arithmetic lives in ``functionals``."""
+    F_sm = _tagged("sm", lambda gc_vec, nb: functionals.F_value("sm", gc_vec, nb))
+    F_re = _tagged("re", lambda gc_vec, nb: functionals.F_value("re", gc_vec, nb))
+    F_ss = _tagged("ss", lambda gc_vec, nb: functionals.F_value("ss", gc_vec, nb))
 
-    @staticmethod
-    def F_re(gc_vec, nb):
-        F = numpy.complex128(0)
-        for a in range(nb):
-            F -= gc_vec[a].real
-        return F
 
-    @staticmethod
-    def F_ss(gc_vec, nb):
-        F = numpy.complex128(0)
-        for a in range(nb):
-            F -= gc_vec[a] * gc_vec[a].conjugate()
-        return F
+def _a_of(kind):
+    def a(psi_init, chi_init, dx, nb, nlevs, np):
+        assert len(psi_init) == nb and len(psi_init.psis[0].f) == nlevs and psi_init.psis[0].f[0].size == np
+        return functionals.a_value(kind, psi_init.as_array(), chi_init.as_array(), dx)
+    return _tagged(kind, a)
 
 
 class _aF_type:
-    @staticmethod
-    def a_sm(psi_init, chi_init, dx, nb, nlevs, np):
-        a = numpy.zeros(nb, dtype=numpy.complex128)
-        for va in range(nb):
-            for v in range(nb):
-                for n in range(nlevs):
-                    a[va] += math_base.cprod(psi_init.psis[v].f[n], chi_init.psis[v].f[n], dx, np)
-        return a
-
-    @staticmethod
-    def a_re(psi_init, chi_init, dx, nb, nlevs, np):
-        return numpy.full(nb, numpy.complex128(0.5))
-
-    @staticmethod
-    def a_ss(psi_init, chi_init, dx, nb, nlevs, np):
-        a = numpy.zeros(nb, dtype=numpy.complex128)
-        for v in range(nb):
-            for n in range(nlevs):
-                a[v] += math_base.cprod(psi_init.psis[v].f[n], chi_init.psis[v].f[n], dx, np)
-        return a
+    """aF_type(psi_init, chi_init, dx, nb, nlevs, np) callables with the reference's names."""
+    a_sm = _a_of("sm")
+    a_re = _a_of("re")
+    a_ss = _a_of("ss")
 
 
 # ----------------------------------------------------------------------------- wavefunctions (task_manager.py:279-337)

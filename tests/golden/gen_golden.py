@@ -570,8 +570,87 @@ def case_shipped(R):
     save("shipped_grid_records", **out)
 
 
+def kat_task_inputs():
+    """Deterministic inputs for the envelope / carrier / functional known-answer vectors.  Shared by the generator
+    (reference functions) and tests/test_host.py, tests/test_oracle.py (ours)."""
+    rng = np.random.default_rng(4711)
+    env_in = [(np.float64(E0), np.float64(t), np.float64(t0), np.float64(sg))
+              for E0, t, t0, sg in zip(rng.uniform(1, 80, 24), rng.uniform(0, 6e-13, 24), rng.uniform(0, 3e-13, 24),
+                                       rng.uniform(2e-14, 1.1e-12, 24))]
+    hf_in = [(np.float64(nu), np.float64(fm), np.float64(t), float(pc), [float(w) for w in rng.uniform(-2, 2, 7)])
+             for nu, fm, t, pc in zip(rng.uniform(1e12, 3e14, 24), rng.uniform(0.8, 1.2, 24), rng.uniform(0, 6e-13, 24),
+                                      rng.choice([1.0, 2.0, 3.0, 4.0], 24))]
+    gcs = [rng.normal(size=nb) + 1j * rng.normal(size=nb) for nb in (1, 2, 2, 4, 4)]
+    bases = [(rng.normal(size=(nb, nl, n)) + 1j * rng.normal(size=(nb, nl, n)),
+              rng.normal(size=(nb, nl, n)) + 1j * rng.normal(size=(nb, nl, n)), np.float64(dx))
+             for nb, nl, n, dx in ((1, 2, 1, 1.0), (2, 2, 1, 1.0), (4, 4, 1, 1.0), (2, 2, 16, 0.125))]
+    return env_in, hf_in, gcs, bases
+
+
+def case_kat_task(R):
+    """Every envelope (task_manager.py:18-70), carrier (72-159), functional (162-207) and 'a' coefficient (209-268) of
+    the reference evaluated on the inputs of ``kat_task_inputs``."""
+    tm = R.task_manager
+    env_in, hf_in, gcs, bases = kat_task_inputs()
+    out = {}
+    L = tm._LaserFields
+    for name, fn in (("zero", L.zero), ("const", L.const), ("gauss", L.laser_field_gauss),
+                     ("sqrsin", L.laser_field_sqrsin), ("maxwell", L.laser_field_maxwell)):
+        out["env_" + name] = np.array([fn(*a) for a in env_in], np.float64)
+    H = tm._LaserFieldsHighFrequencyPart
+    for name, fn in (("exp", H.cexp), ("cos", H.cos), ("sin", H.sin), ("cos_set", H.cos_set), ("sin_set", H.sin_set)):
+        out["hf_" + name] = np.array([fn(*a) for a in hf_in], np.complex128)
+    for k, gc in enumerate(gcs):
+        for name, fn in (("sm", tm._F_type.F_sm), ("re", tm._F_type.F_re), ("ss", tm._F_type.F_ss)):
+            out["F_%s_%d" % (name, k)] = np.complex128(fn(gc, len(gc)))
+    for k, (psi, chi, dx) in enumerate(bases):
+        nb, nl, n = psi.shape
+
+        def basis(arr):
+            b = R.psi_basis.PsiBasis(nb, nl)
+            for v in range(nb):
+                for lv in range(nl):
+                    b.psis[v].f[lv] = arr[v, lv].copy()
+            return b
+        for name, fn in (("sm", tm._aF_type.a_sm), ("re", tm._aF_type.a_re), ("ss", tm._aF_type.a_ss)):
+            out["a_%s_%d" % (name, k)] = np.asarray(fn(basis(psi), basis(chi), dx, nb, nl, n), np.complex128)
+    save("kat_task_functions", **out)
+
+
+def conf_variant(base, **fitter_or_root):
+    """``base`` with root keys (init_guess, init_guess_hf, ...) and fitter keys (F_type, pcos, ...) replaced."""
+    c = copy.deepcopy(base)
+    for k, v in fitter_or_root.items():
+        if k in ("F_type", "pcos", "w_list", "h_lambda", "h_lambda_mode", "epsilon"):
+            c["fitter"][k] = v
+        elif k in ("sigma", "t0", "E0", "nu_L"):
+            c["fitter"]["propagation"][k] = v
+        else:
+            c[k] = v
+    return c
+
+
+def case_fitter_variants(R):
+    """The functionals and pulse shapes no shipped configuration uses: F_re and F_ss with
+    their 'a' coefficients, the maxwell and const envelopes, the cos and sin carriers -- each as a whole
+    unitary-transformation optimisation of the well-conditioned 2-level Jx system (3 iterations, nt = 400), driven
+    through the reference's FittingSolver like every other fixture."""
+    base = conf_ut_jx(400, 3)
+    for name, user in (
+            ("fit_ut_jx_re", conf_variant(base, F_type="re")),
+            ("fit_ut_jx_ss", conf_variant(base, F_type="ss")),
+            ("fit_ut_jx_maxwell_cos", conf_variant(base, init_guess="maxwell", init_guess_hf="cos", pcos=1.0,
+                                                   t0_auto=True)),
+            ("fit_ut_jx_const_sin", conf_variant(base, init_guess="const", init_guess_hf="sin", pcos=1.0))):
+        conf, tm, fs, rep, err = run_fitter(R, user, 100)
+        out = pack_fitter(rep, fs, tm, err, ("iter_0b/basis_0", "iter_3f/basis_1"))
+        out["conf_json"] = np.array(repr(user))
+        save(name, **out)
+
+
 CASES = {"kat": case_kat, "one_step": case_one_step, "fitter_grid": case_fitter_grid,
-         "fitter_nlevel": case_fitter_nlevel, "fitter_local": case_fitter_local, "report_tables": case_report_tables, "shipped": case_shipped}
+         "fitter_nlevel": case_fitter_nlevel, "fitter_local": case_fitter_local, "report_tables": case_report_tables, "shipped": case_shipped,
+         "kat_task": case_kat_task, "fitter_variants": case_fitter_variants}
 
 if __name__ == "__main__":
     R = load_reference()

@@ -151,7 +151,9 @@ def test_propagation_solver_drop_in(golden):
     _compare_records(rec.rows, g, "iter_0f__basis_0", float(tm.dx), 1e-10)
 
 
-@pytest.mark.parametrize("name,mod", [("fit_krotov_256", 40), ("fit_single_harm", 10), ("fit_ut_jx", 100)])
+@pytest.mark.parametrize("name,mod", [("fit_krotov_256", 40), ("fit_single_harm", 10), ("fit_ut_jx", 100),
+                                      ("fit_ut_jx_re", 100), ("fit_ut_jx_ss", 100), ("fit_ut_jx_maxwell_cos", 100),
+                                      ("fit_ut_jx_const_sin", 100)])
 def test_fitting_solver_drop_in(golden, name, mod):
     """S3: FittingSolver(...).time_propagation(dx, x, t_step, t_list) with recording reporters -- the
     call sequence of tests/functional_tests.py:120-133 -- against the reference's iteration rows and
@@ -256,3 +258,48 @@ def test_newcheb_command_line(tmp_path):
     bad = subprocess.run([sys.executable, "-m", "qcontrol_b200.newcheb", "--json_task", str(tmp_path / "task.json")],
                          cwd=root, capture_output=True, text=True, timeout=120)
     assert bad.returncode == 2 and "Usage" in bad.stdout
+
+
+def test_two_fitting_solvers_from_a_thread_pool(golden):
+    """The reference farms its jobs over ThreadPoolExecutor (newcheb.py:656-659): two FittingSolvers running at the
+    same time from two host threads -- each thread gets its own context and stream (phys_base.default_context is
+    thread-local) -- must both reproduce the reference's tables; the one-step drop-ins prop_cpu / hamil2D called
+    concurrently on the SAME functor object must not mix their states."""
+    from concurrent.futures import ThreadPoolExecutor
+    from qcontrol_b200 import fitter, phys_base
+    from qcontrol_b200.psi_basis import Psi
+
+    def job(name):
+        g = golden(name)
+        conf, tm = _setup(ast.literal_eval(str(g["conf_json"])))
+        rep = _Rec(100)
+        fs = fitter.FittingSolver(conf.fitter, conf.task_type, conf.T, conf.np, conf.L, tm.init_dir, tm.ntriv, tm.psi0,
+                                  tm.psif, tm.v, tm.akx2, tm.F_goal, tm.laser_field, tm.laser_field_hf, tm.F_type,
+                                  tm.aF_type, tm.hamil2D, rep, None, None)
+        with contextlib.redirect_stdout(io.StringIO()):
+            fs.time_propagation(tm.dx, tm.x, tm.t_step, tm.t_list)
+        return np.array([r[:5] for r in rep.iter_rows], float), id(phys_base.default_context())
+
+    names = ["fit_krotov_256", "fit_ut_jx", "fit_krotov_256", "fit_ut_jx"]
+    with ThreadPoolExecutor(2) as pool:
+        results = list(pool.map(job, names))
+    for name, (tab, _) in zip(names, results):
+        ref = golden(name)["iter_tab"]
+        assert tab.shape == ref.shape and np.allclose(tab[:, 1:], ref[:, 1:], rtol=1e-9, atol=1e-12), name
+    assert len({cid for _, cid in results}) == 2          # one context per worker thread
+    assert id(phys_base.default_context()) not in {cid for _, cid in results}
+
+    g = golden("one_step_krotov")
+    import tests.golden.gen_golden as gg
+    conf, tm = _setup(gg.conf_krotov(2000, 1))
+
+    def step(k):
+        psi = Psi(f=[g["psi_in"][0].copy() * (1 + k), g["psi_in"][1].copy() * (1 + k)], lvls=2)
+        out = phys_base.prop_cpu(psi=psi, hamil2D=tm.hamil2D, t_sc=float(g["t_sc"]), nch=int(g["nch"]), np=conf.np,
+                                 emin=float(g["emin"]), emax=float(g["emax"]), E=np.float64(g["E_f"]), eL=float(g["eL"]),
+                                 E_full=np.float64(g["E_f"]), orig=False)
+        return l2(out.as_array(), g["psi_out_f"] * (1 + k), float(g["dx"])) / (1 + k)
+
+    with ThreadPoolExecutor(4) as pool:
+        errs = list(pool.map(step, range(16)))
+    assert max(errs) <= 1e-10, errs

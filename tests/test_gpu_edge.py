@@ -206,7 +206,7 @@ def test_np4096_krotov_vs_oracle(ctx):
     gb.close()
 
 
-@pytest.mark.parametrize("np_,batch", [(256, 1300), (512, 650), (1024, 600)])
+@pytest.mark.parametrize("np_,batch", [(256, 1300), (512, 650), (1024, 600), (2048, 1200)])
 def test_propagate_host_pipeline(ctx, np_, batch):
     """qc_propagate_host (host buffers in, host buffers out; the call bench.py's e2e figure times): batches larger
     than one pipeline chunk (592 runs; 1184 at np = 256) are cut into chunks over three streams -- at np <= 512 the
@@ -226,6 +226,7 @@ def test_propagate_host_pipeline(ctx, np_, batch):
     dev = pl.get_state()
     assert np.abs(hout - dev).max() <= 1e-13          # packed / unpacked forms differ in the order of the norm sums
     assert np.abs(hout - hin).max() > 1e-3            # it did propagate
+    # (2048, 1200) is the shape bench.py's e2e figure is quoted on: two full pipeline chunks and a tail of 16 runs
     for b in (0, 591, 592, batch - 1) if np_ > 256 else (0, 1183, 1184, batch - 1):
         run = pbs[b]
         pb = qo.Problem(task_type="trans_wo_control", hamil="ntriv", ntriv=1, np_=np_, nlevs=2, nb=1, L=run.L, T=run.T,
@@ -239,3 +240,70 @@ def test_propagate_host_pipeline(ctx, np_, batch):
         err = float(np.sqrt(run.dx * np.sum(np.abs(hout[b, 0] - st.psi) ** 2)))
         assert err <= 1e-10 * nt, (np_, b, err)
     gb.close()
+
+
+def test_krotov_stopping_rule_like_reference(ctx):
+    """The iteration budget of a Krotov run as the reference spends it (fitter.py:441-489, 537-562):
+    (a) goal met by the initial guess at iteration 0 -> no row at all, no backward sweep; (b) otherwise the loop
+    condition is tested on the Fsm of the BACKWARD sweep (zero), so a run whose forward functional is within epsilon
+    at a later iteration still runs to iter_max; (c) the divergence guard sees the same zeros and stops the run at
+    iter_mid_2 with the reference's ValueError text.  All three in ONE ragged batch, each against the oracle."""
+    from qcontrol_b200 import control
+    cases = []
+    for eps, q, mid1, mid2, itmax in ((0.9999, 0.0, 0, 1, 3), (1e-8, 0.0, 0, 1, 3), (1e-8, 0.75, 1, 2, 3)):
+        user = conf_krotov(60, itmax, np_=256)
+        user["fitter"].update(epsilon=eps, q=q, iter_mid_1=mid1, iter_mid_2=mid2)
+        cases.append(qo.make_problem(user))
+    gb = control.GridBatch(cases, ctx=ctx)
+    hist = gb.run_krotov()
+    for b, pb in enumerate(cases):
+        f = qo.Fitter(pb)
+        err = ""
+        try:
+            f.run()
+        except ValueError as e:
+            err = str(e)
+        want = _rows(f.rows)
+        got = _rows(hist[b])
+        assert got.shape == want.shape, (b, got.shape, want.shape)
+        if len(want):
+            assert np.allclose(got, want, rtol=1e-9, atol=0), (b, got - want)
+        assert gb.errors[b] == err, (b, gb.errors[b], err)
+    assert [len(h) for h in hist] == [0, 4, 3]
+    gb.close()
+
+
+def test_get_traj_beyond_the_2gib_pitch(ctx):
+    """qc_get_traj of a grid plan whose run stride (nt_max + 1) * np * 16 B exceeds 2 GiB (the shipped Krotov input:
+    230001 x 1024 x 16 B = 3.77 GB): the slice is gathered on the device and copied contiguously."""
+    from qcontrol_b200 import engine
+    np_, nt_max, batch = 2048, 70000, 2
+    assert (nt_max + 1) * np_ * 16 > 2 ** 31
+    pl = engine.Plan(ctx, engine.HAMIL_NONTRIV, np_, 2, 1, 64, batch, nt_max, store_traj=True)
+    rng = np.random.default_rng(5)
+    psi = rng.standard_normal((batch, 1, 2, np_)) + 1j * rng.standard_normal((batch, 1, 2, np_))
+    pl.set_state(psi)
+    for index, level in ((nt_max, 0), (12345, 1), (0, 0)):
+        pl.record_state(0, index, level)
+        got = pl.get_traj(0, index)
+        assert np.array_equal(got[:, 0], psi[:, 0, level]), (index, level)
+    pl.close()
+
+
+def test_memory_sized_sub_batches(ctx):
+    """newcheb.memory_chunks against the real device: every chunk's plan can actually be created next to the
+    free-memory figure it was sized for, and the footprint bound is not below what the plan allocates."""
+    from qcontrol_b200 import engine
+    free0, total = ctx.mem_info()
+    assert 0 < free0 <= total
+    est = engine.plan_footprint(engine.HAMIL_NONTRIV, 1024, 2, 1, 64, 64, 2000, True, True)
+    pl = engine.Plan(ctx, engine.HAMIL_NONTRIV, 1024, 2, 1, 64, 64, 2000, hf_hide=True, store_traj=True)
+    for slot in range(4):
+        pl.snapshot_set(slot, np.zeros(pl.state_shape, np.complex128))
+    pl.set_exp_L(np.ones((64, 2001), np.complex128), 0)
+    pl.set_exp_L(np.ones((64, 2001), np.complex128), 1)
+    ctx.synchronize()
+    used = free0 - ctx.mem_info()[0]
+    pl.close()
+    assert used <= est + (64 << 20), (used, est)          # the allocator rounds to 2 MiB pages
+    assert used >= 0.5 * est

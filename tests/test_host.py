@@ -10,7 +10,8 @@ import pytest
 from oracle import qc_oracle as qo
 
 CONFS = ["fit_single_harm", "fit_single_morse", "fit_trans_woc", "fit_krotov_256", "fit_krotov_1024", "fit_ut_jx",
-         "fit_ut_jx_4lvls", "fit_ut_jz", "fit_ut_s2s", "fit_pi_pulse"]
+         "fit_ut_jx_4lvls", "fit_ut_jz", "fit_ut_s2s", "fit_pi_pulse", "fit_ut_jx_re", "fit_ut_jx_ss",
+         "fit_ut_jx_maxwell_cos", "fit_ut_jx_const_sin"]
 
 
 def _load(user):
@@ -59,6 +60,46 @@ def test_task_setup_bit_exact(golden, name):
     assert float(tm.dx) == float(g["dx"]) and float(tm.t_step) == float(g["t_step"])
 
 
+def test_task_functions_kat(golden):
+    """The product's envelopes, carriers (qcontrol_b200.task_manager), functionals and 'a' coefficients
+    (qcontrol_b200.functionals, the one definition task_manager and control share) against the reference's own
+    functions on the inputs of gen_golden.kat_task_inputs: bit-exact.  Covers the variants no shipped configuration
+    uses: maxwell / const envelopes, cos / sin carriers, F_re / F_ss, a_re / a_ss (task_manager.py:24-268)."""
+    from qcontrol_b200 import functionals, task_manager as tmod
+    from qcontrol_b200.psi_basis import PsiBasis
+    from tests.golden.gen_golden import kat_task_inputs
+    g = golden("kat_task_functions")
+    env_in, hf_in, gcs, bases = kat_task_inputs()
+    L, H = tmod._LaserFields, tmod._LaserFieldsHighFrequencyPart
+    for name, fn in (("zero", L.zero), ("const", L.const), ("gauss", L.laser_field_gauss),
+                     ("sqrsin", L.laser_field_sqrsin), ("maxwell", L.laser_field_maxwell)):
+        assert np.array_equal(np.array([fn(*a) for a in env_in], np.float64), g["env_" + name]), name
+    for name, fn in (("exp", H.cexp), ("cos", H.cos), ("sin", H.sin), ("cos_set", H.cos_set), ("sin_set", H.sin_set)):
+        assert np.array_equal(np.array([fn(*a) for a in hf_in], np.complex128), g["hf_" + name]), name
+    for kind in functionals.KINDS:
+        F_ref_style = getattr(tmod._F_type, "F_" + kind)
+        a_ref_style = getattr(tmod._aF_type, "a_" + kind)
+        assert functionals.kind_of(F_ref_style) == kind
+        for k, gc in enumerate(gcs):
+            want = g["F_%s_%d" % (kind, k)]
+            assert np.complex128(F_ref_style(gc, len(gc))) == want and functionals.F_value(kind, gc, len(gc)) == want
+            assert abs(functionals.F_batch(kind, gc[None, :])[0] - want.real) <= 1e-14 * max(1.0, abs(want))
+        for k, (psi, chi, dx) in enumerate(bases):
+            want = g["a_%s_%d" % (kind, k)]
+            nb, nl, n = psi.shape
+            assert np.array_equal(a_ref_style(PsiBasis.from_array(psi), PsiBasis.from_array(chi), dx, nb, nl, n), want)
+            assert np.array_equal(functionals.a_value(kind, psi, chi, dx), want)
+            assert np.allclose(functionals.a_batch(kind, psi[None], chi[None], np.array([dx]))[0], want, rtol=1e-13, atol=1e-13)
+    # the vectorised set-up path of big batches (control._env_vec / _hf_vec) is the same formula up to libm rounding
+    from qcontrol_b200 import control
+    for name in ("zero", "const", "gauss", "sqrsin", "maxwell"):
+        got = np.array([control._env_vec(name, a[0], np.array([a[1]]), a[2], a[3])[0] for a in env_in])
+        assert np.allclose(got, g["env_" + name], rtol=1e-13, atol=0), name
+    for name in ("exp", "cos", "sin", "cos_set", "sin_set"):
+        got = np.array([control._hf_vec(name, a[0] * a[1], np.array([a[2]]), a[3], a[4])[0] for a in hf_in])
+        assert np.allclose(got, g["hf_" + name], rtol=1e-11, atol=1e-12), name
+
+
 def test_config_semantics():
     from qcontrol_b200.config import TaskRootConfiguration as T
     c = T()
@@ -105,6 +146,44 @@ def test_energy_window_matches_reference(golden, name):
                                                                   float(g["eL"]))
     _, _, t_b, _ = control.energy_window(pb, control.BACKWARD)
     assert float(t_b) == -float(t_sc)
+
+
+def test_report_stride_is_the_gcd_of_the_member_moduli():
+    """A fan-out reporter whose members keep every 100th and every 30th step must be visited at every multiple of
+    gcd = 10 -- with the minimum (30) step 100 would never be seen."""
+    from types import SimpleNamespace as NS
+    from qcontrol_b200 import fitter
+    member = lambda mod: NS(conf=NS(mod_fileout=mod))
+    assert fitter.report_stride(member(40)) == 40
+    assert fitter.report_stride(NS(reps=[member(100), member(30)])) == 10
+    assert fitter.report_stride(NS(reps=[member(100), NS(reps=[member(75)])])) == 25
+    assert fitter.report_stride(NS(reps=[])) == 0            # nobody keeps anything
+
+
+def test_memory_sized_sub_batches_host_logic():
+    """newcheb.memory_chunks: runs longest first, a sub-batch per memory budget, every run exactly once; the
+    footprint bound of the shipped Krotov input (nt = 230000, np = 1024) is 2 x 3.77 GB of trajectories + state."""
+    from qcontrol_b200 import engine, newcheb
+    from tests.golden.gen_golden import conf_krotov, conf_single_morse
+    confs = []
+    for nt in (100, 400, 250, 400, 50, 300):
+        c, _ = _load(conf_krotov(nt, 2, np_=1024))
+        confs.append(c)
+    one = engine.plan_footprint(engine.HAMIL_NONTRIV, 1024, 2, 1, 64, 1, 400, True, True)
+    two = engine.plan_footprint(engine.HAMIL_NONTRIV, 1024, 2, 1, 64, 2, 400, True, True)
+    assert two > one > 2 * 401 * 1024 * 16
+    chunks = newcheb.memory_chunks(confs, list(range(6)), free_bytes=two / 0.8 + 1, fraction=0.8)
+    assert sorted(i for c in chunks for i in c) == list(range(6))
+    assert chunks[0] == [1, 3] and all(len(c) <= 3 for c in chunks) and len(chunks) >= 3
+    assert newcheb.memory_chunks(confs, list(range(6)), free_bytes=1e12) == [list(range(6))]
+    with pytest.raises(MemoryError):
+        newcheb.memory_chunks(confs, [1], free_bytes=one / 2)
+    shipped = engine.plan_footprint(engine.HAMIL_NONTRIV, 1024, 2, 1, 64, 1, 230000, True, True)
+    assert 7.5e9 < shipped < 7.8e9
+    # a prescribed-field task has no trajectory buffers: the shipped filtering length costs megabytes, not 52 GB
+    c, _ = _load(conf_single_morse(40))
+    c.fitter.propagation.nt = 800000
+    assert newcheb.memory_chunks([c], [0], free_bytes=1e9) == [[0]]
 
 
 def test_substitution_expansion_order():

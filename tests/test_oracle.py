@@ -160,7 +160,8 @@ def _run_and_compare(pb, g, keep=(), tol=0.0):
 
 
 @pytest.mark.parametrize("name", ["fit_ut_jx", "fit_ut_jx_4lvls", "fit_ut_jz", "fit_ut_s2s", "fit_ut_jx_4lvls_wc",
-                                  "fit_ut_jz_wc", "fit_ut_s2s_wc"])
+                                  "fit_ut_jz_wc", "fit_ut_s2s_wc", "fit_ut_jx_re", "fit_ut_jx_ss",
+                                  "fit_ut_jx_maxwell_cos", "fit_ut_jx_const_sin"])
 def test_unit_transform_bitexact(golden, name):
     """Whole optimisation loops on N-level systems: backward/forward sweeps,
     field update from the stored trajectory, dynamic h_lambda, F / E_int / J."""
@@ -168,6 +169,26 @@ def test_unit_transform_bitexact(golden, name):
     pb, _ = _problem_from(g)
     _check_setup(pb, g)
     _run_and_compare(pb, g)
+
+
+def test_task_functions_kat(golden):
+    """Every envelope, carrier, functional and 'a' coefficient of the oracle against values computed by the
+    reference's own functions (task_manager.py:18-268) on the inputs of gen_golden.kat_task_inputs: bit-exact."""
+    from tests.golden.gen_golden import kat_task_inputs
+    g = golden("kat_task_functions")
+    env_in, hf_in, gcs, bases = kat_task_inputs()
+    for name in ("zero", "const", "gauss", "sqrsin", "maxwell"):
+        got = np.array([qo.ENVELOPES[name](*a) for a in env_in], np.float64)
+        assert np.array_equal(got, g["env_" + name]), name
+    for name in ("exp", "cos", "sin", "cos_set", "sin_set"):
+        got = np.array([qo.CARRIERS[name](*a) for a in hf_in], np.complex128)
+        assert np.array_equal(got, g["hf_" + name]), name
+    for kind in ("sm", "re", "ss"):
+        F_fn, a_fn = qo.FUNCTIONALS[kind]
+        for k, gc in enumerate(gcs):
+            assert np.complex128(F_fn(gc, len(gc))) == g["F_%s_%d" % (kind, k)], (kind, k)
+        for k, (psi, chi, dx) in enumerate(bases):
+            assert np.array_equal(a_fn(psi, chi, dx), g["a_%s_%d" % (kind, k)]), (kind, k)
 
 
 def test_pi_pulse_bitexact(golden):
