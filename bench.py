@@ -7,21 +7,31 @@ One bench "step" is one Krotov iteration of the whole batch: forward sweep with 
 update from the stored backward trajectory, goal overlaps, chi(T) construction, backward sweep
 (fitter.py:441-489), all device-resident.  grid-pt*timesteps = runs * np * (2*nt) per step.
 
-    python bench.py --gpus N --steps K --warmup W            # this framework
-    python bench.py --impl reference --steps K --warmup W    # the CPU path (numpy oracle port) on host cores
+    python bench.py --gpus N --steps K --warmup W            # this framework (N > 1: re-launches itself under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU path on the host cores
 
-Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions of value / e2e /
-roofline / cpu_baseline.
+Prints ONE JSON line (rank 0).  Beside the contract's keys the GPU line carries
+  roofline      the Krotov forward sweep kernel against the FP64 peak measured in the same process
+  e2e           qc_propagate_host: host buffers in / out through the C ABI (prescribed-field sweep: NOT the Krotov
+                iteration `value` times -- it moves every wavefunction over PCIe both ways, the iteration does not)
+  e2e_api       newcheb.run_variants: the call a user of the reference makes, from JSON dictionaries to gathered
+                iteration tables, wall clock with task set-up, Newton tables, step scalars and plan upload
+  extra.ut_jx_tsweep   kernel B on the reference's 400-run batch input_batch/inp_Jx_250-19000fs_25runs.json, runs
+                sharded over the ranks by batch.lpt_shards, results through batch.gather_results (NCCL)
+  cpu_baseline  the reference (oracle/_ref, kind "reference") or the numpy port (kind "port") on the host cores
+See DESIGN.md "Measurement" for the definitions.
 """
 from __future__ import annotations
 
 import argparse
+import importlib
 import json
 import math
 import os
 import sys
 import threading
 import time
+import types
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -32,6 +42,7 @@ import numpy as np
 METRIC = "wavefunction grid-pt*timesteps/s"
 UNIT = "grid-pt*timesteps/s"
 NP_, NCH, NLEVS = 2048, 64, 2
+HBM_PEAK_GBS_FALLBACK = 6650.0
 
 
 def flops_per_step(np_=NP_, nlevs=NLEVS, nch=NCH, overlap=True):
@@ -39,14 +50,94 @@ def flops_per_step(np_=NP_, nlevs=NLEVS, nch=NCH, overlap=True):
     return (nch - 1) * nlevs * np_ * (10 * math.log2(np_) + 18) + 18 * nlevs * np_ + (8 * np_ if overlap else 0)
 
 
+def bench_config(a):
+    """The ``config`` object of the JSON line -- the SAME in both arms (the driver compares them)."""
+    return {"workload": "krotov_batch_8192x2048", "runs_per_gpu": a.runs, "np": NP_, "nlevs": NLEVS, "nch": NCH,
+            "nt": a.nt, "step": "one Krotov iteration (forward + backward sweep) of every run",
+            "l2": "working set (trajectories + state, %.1f GB) exceeds L2" % (
+                (2 * (a.nt + 1) * a.runs * NP_ * 16 + 3 * a.runs * 2 * NP_ * 16) / 1e9)}
+
+
+def hbm_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return HBM_PEAK_GBS_FALLBACK, "fallback of B200_PROFILING.md"
+
+
+def numpy_only(name):
+    """``qcontrol_b200.<name>`` WITHOUT importing the package: its __init__ loads the CUDA library, and the CPU arm
+    must not map it (round-1 verdict: the reference arm's process listed the repo's .so).  Only modules that import
+    nothing but numpy and their numpy-only siblings can be loaded this way (synthetic, phys_consts)."""
+    pkg = sys.modules.get("qcb200_nolib")
+    if pkg is None:
+        pkg = types.ModuleType("qcb200_nolib")
+        pkg.__path__ = [os.path.join(ROOT, "qcontrol_b200")]
+        sys.modules["qcb200_nolib"] = pkg
+    return importlib.import_module("qcb200_nolib." + name)
+
+
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the numpy port of the reference path (oracle/), one process per core
+# CPU arm: the reference itself (oracle/_ref, an unmodified copy) or the numpy port (oracle/qc_oracle.py),
+# one persistent process per host core, each propagating one run of the bench workload
 # ------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    nsteps, seed = args
+def _make_stepper(kind, seed, nt_total):
+    """callable() that advances one run of the bench workload by one time step."""
+    run = numpy_only("synthetic").krotov_batch(1, NP_, nt_total, NCH, seed=seed)[0]
+    if kind == "reference":
+        from oracle import ref_loader
+        R = ref_loader.load_reference(ref_loader.available_root())
+        import contextlib
+        import copy
+        import io
+        P = R.propagation.PropagationSolver
+        with contextlib.redirect_stdout(io.StringIO()):
+            conf = R.config.TaskRootConfiguration()
+            conf.load({"task_type": "trans_wo_control", "pot_type": "morse", "wf_type": "morse", "hamil_type": "ntriv",
+                       "init_guess": "gauss", "init_guess_hf": "exp", "nb": 1, "nlevs": 2, "T": float(run.T), "L": run.L,
+                       "np": NP_, "fitter": {"impulses_number": 1, "mod_log": 10 ** 9, "hf_hide": True,
+                                             "propagation": {"m": run.m, "nch": NCH, "nt": nt_total, "E0": float(run.E0),
+                                                             "t0": float(run.t0), "sigma": float(run.sigma),
+                                                             "nu_L": float(run.nu_L)}}})
+        cp = conf.fitter.propagation
+        v = [(np.float64(run.vmin[n]), np.asarray(run.v[n], np.float64)) for n in range(2)]
+        hamil = R.hamil_2d.Hamil2DNonTrivial(v, run.akx2, NP_, 0.0, 0.0, 1.0, 1)
+        gauss = R.task_manager._LaserFields.laser_field_gauss
+        cexp = R.task_manager._LaserFieldsHighFrequencyPart.cexp
+
+        class Null(R.reporter.PropagationReporter):
+            def __init__(self):
+                super().__init__("", 2)
+
+            def open(self):
+                return self
+
+            def close(self):
+                pass
+
+            def print_time_point_prop(self, *args):
+                pass
+
+        def basis_vec(arr):
+            return R.psi_basis.Psi(f=[arr[0].copy(), arr[1].copy()], lvls=2)
+
+        with contextlib.redirect_stdout(io.StringIO()):
+            s = P(T=conf.T, np=NP_, L=conf.L, _warning_collocation_points=None, _warning_time_steps=None, reporter=Null(),
+                  hamil2D=hamil, laser_field_envelope=lambda prop, stat, dyn: gauss(cp.E0, dyn.t, cp.t0, cp.sigma),
+                  laser_field_hf=lambda fm, t, pcos, w: cexp(run.nu, fm, t, pcos, w),
+                  freq_multiplier=lambda dyn, stat: np.float64(1.0),
+                  dynamic_state_factory=lambda l, t, psi, psi_omega, E, fm, d: P.DynamicState(
+                      l, t, copy.deepcopy(psi), copy.deepcopy(psi_omega), E, fm, d),
+                  pcos=conf.fitter.pcos, w_list=conf.fitter.w_list, mod_log=10 ** 9, ntriv=1, hf_hide=True, conf_prop=cp)
+            s.start(v, run.akx2, run.dx, run.x, run.t_step, basis_vec(run.psi0[0]), basis_vec(run.psif[0]),
+                    P.Direction.FORWARD)
+
+        def step():
+            with contextlib.redirect_stdout(io.StringIO()):
+                s.step(0.0)
+        return step
     from oracle import qc_oracle as qo
-    from qcontrol_b200.synthetic import krotov_batch  # plain numpy set-up code; loads no CUDA library symbols it calls
-    run = krotov_batch(1, NP_, nsteps, NCH, seed=seed)[0]
     pb = qo.Problem(task_type="trans_wo_control", hamil="ntriv", ntriv=1, np_=NP_, nlevs=2, nb=1, L=run.L, T=run.T,
                     dx=run.dx, x=run.x, v=run.v, vmin=run.vmin, akx2=run.akx2, psi0=run.psi0, psif=run.psif, m=run.m,
                     nch=NCH, nt=run.nt, E0=run.E0, t0=run.t0, sigma=run.sigma, nu_L=run.nu_L, nu=run.nu,
@@ -54,21 +145,86 @@ def _cpu_worker(args):
     st = qo.Stepper(pb, lambda s: pb.laser_field(pb.E0, s.t, pb.t0, pb.sigma), instrument=False)
     st._coeffs = lambda t_sc: qo.points(pb.nch, t_sc)     # the reference rebuilds the table every step (phys_base.py:155)
     st.start(pb.psi0[0], pb.psif[0], qo.FORWARD)
-    t0 = time.perf_counter()
-    for _ in range(nsteps):
-        st.step(np.float64(0.0))
-    return time.perf_counter() - t0
+    return lambda: st.step(np.float64(0.0))
 
 
-def cpu_rate(nsteps_per_proc, procs):
-    """grid-pt*timesteps/s of the oracle port over `procs` processes, each propagating one run."""
-    import multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    t0 = time.perf_counter()
-    with ctx.Pool(procs) as pool:
-        pool.map(_cpu_worker, [(nsteps_per_proc, 100 + i) for i in range(procs)])
-    wall = time.perf_counter() - t0
-    return procs * NP_ * nsteps_per_proc / wall, wall
+def _cpu_worker(conn, kind, seed, nt_total):
+    try:
+        step = _make_stepper(kind, seed, nt_total)
+        step()                                   # first-touch / import costs stay outside every timed region
+        conn.send(("ready", None))
+        while True:
+            n = conn.recv()
+            if n is None:
+                break
+            t0 = time.perf_counter()
+            for _ in range(n):
+                step()
+            conn.send(("done", time.perf_counter() - t0))
+    except Exception as e:                       # noqa: BLE001 -- reported to the parent, which raises
+        conn.send(("error", repr(e)))
+    finally:
+        conn.close()
+
+
+class CpuFarm:
+    """One persistent process per core, each owning one run; ``run(n)`` advances every run by n time steps at the
+    same time and returns the seconds of the slowest worker.  The pool is created ONCE (process start-up, imports
+    and problem set-up are not timed)."""
+
+    def __init__(self, kind, procs, nt_total):
+        import multiprocessing as mp
+        ctx = mp.get_context("spawn")
+        self.kind, self.procs, self.workers = kind, procs, []
+        for i in range(procs):
+            parent, child = ctx.Pipe()
+            p = ctx.Process(target=_cpu_worker, args=(child, kind, 100 + i, nt_total), daemon=True)
+            p.start()
+            child.close()
+            self.workers.append((p, parent))
+        for _, c in self.workers:
+            tag, val = c.recv()
+            if tag != "ready":
+                self.close()
+                raise RuntimeError("CPU worker failed: %s" % val)
+
+    def run(self, nsteps):
+        for _, c in self.workers:
+            c.send(nsteps)
+        worst = 0.0
+        for _, c in self.workers:
+            tag, val = c.recv()
+            if tag != "done":
+                raise RuntimeError("CPU worker failed: %s" % val)
+            worst = max(worst, val)
+        return worst
+
+    def rate(self, nsteps):
+        return self.procs * NP_ * nsteps / self.run(nsteps)
+
+    def close(self):
+        for p, c in self.workers:
+            try:
+                c.send(None)
+            except Exception:
+                pass
+        for p, _ in self.workers:
+            p.join(timeout=10)
+            if p.is_alive():
+                p.terminate()
+
+
+def cpu_kind():
+    from oracle import ref_loader
+    return "reference" if ref_loader.available_root() else "port"
+
+
+def cpu_sample_text(kind, cores, nsteps):
+    what = ("the UNMODIFIED reference (oracle/_ref: PropagationSolver.step with its instrumentation and per-step "
+            "Newton table, as the reference always computes them)" if kind == "reference" else
+            "numpy port of the reference path (oracle/qc_oracle.py, no instrumentation; /root/reference is absent)")
+    return ("%d processes x 1 run x %d time steps of the bench workload (np=%d, nch=%d, 2 levels, hf_hide, prescribed "
+            "field) at the same time; %s; process start-up and set-up not timed" % (cores, nsteps, NP_, NCH, what))
 
 
 def run_reference_arm(a):
@@ -76,24 +232,22 @@ def run_reference_arm(a):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    kind = cpu_kind()
     nsteps = a.cpu_steps
-    for _ in range(a.warmup if a.warmup < 2 else 1):
-        cpu_rate(max(2, nsteps // 8), cores)
-    vals = []
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        r, _w = cpu_rate(nsteps, cores)
-        vals.append(r)
-    wall = time.perf_counter() - t0
-    v = float(np.mean(vals))
-    sample = "%d processes x 1 run x %d time steps (np=%d, nch=%d, 2 levels, hf_hide) per bench step; pool start-up included" % (
-        cores, nsteps, NP_, NCH)
+    farm = CpuFarm(kind, cores, nsteps * (a.steps + a.warmup) + 2)
+    try:
+        for _ in range(a.warmup):
+            farm.run(nsteps)
+        secs = [farm.run(nsteps) for _ in range(a.steps)]
+    finally:
+        farm.close()
+    total = float(sum(secs))
+    v = cores * NP_ * nsteps * a.steps / total
     line = {"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": 1e3 * wall / max(a.steps, 1), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "krotov_batch_8192x2048", "np": NP_, "nch": NCH, "nlevs": NLEVS,
-                       "impl_note": "numpy port of the reference path (oracle/qc_oracle.py); the reference is pure Python and /root/reference does not travel"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "warmup": a.warmup, "ms_per_step": 1e3 * total / max(a.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": bench_config(a),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": cpu_sample_text(kind, cores, nsteps) + " (one bench step of this arm)"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -136,6 +290,182 @@ class ClockSampler(threading.Thread):
     def summary(self):
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# extra: the reference's own batch (BASELINE config 4) on kernel B, sharded over the ranks
+# ------------------------------------------------------------------------------------------------
+UT_T_LIST = [2.5E-13, 11.8E-12, 13.4E-12, 14.0E-12, 15.0E-12, 16.6E-12, 16.8E-12, 17.0E-12, 17.6E-12, 17.8E-12, 18.0E-12,
+             18.2E-12, 18.4E-12, 18.6E-12, 18.8E-12, 19.0E-12]
+
+
+def ut_jx_template(iterations):
+    """input_batch/inp_Jx_250-19000fs_25runs.json (25 run ids x 16 durations = 400 runs; np = 1, nch = 8,
+    nb = nlevs = 2, nt = floor(T / 2 fs) = 125 ... 9500) with a FIXED iteration count: epsilon -> 0, iter_max =
+    iterations - 1, divergence guard off, so that every run does the same amount of work on every box."""
+    return {"run_id": {"@SUBST:LIST": ["ut/run%d" % i for i in range(1, 26)]},
+            "task_type": "optimal_control_unit_transform", "pot_type": "none", "wf_type": "const", "hamil_type": "BH_model",
+            "lf_aug_type": "x", "init_guess": "sqrsin", "init_guess_hf": "sin_set", "nb": 2, "T": {"@SUBST:LIST": UT_T_LIST},
+            "np": 1, "L": 1.0, "Du": 1.0, "U": 30.0, "W": 30.0, "delta": 15.0, "nt_auto": True, "sigma_auto": True,
+            "nu_L_auto": True,
+            "fitter": {"epsilon": 1e-30, "impulses_number": 1, "iter_max": iterations - 1, "iter_mid_1": 250,
+                       "iter_mid_2": 300, "q": 0.0, "h_lambda": 0.00005, "h_lambda_mode": "dynamical", "pcos": 2.0,
+                       "hf_hide": False, "propagation": {"nch": 8, "t0": 0.0, "E0": 40.0}, "mod_log": 500}}
+
+
+def ut_jx_tsweep_block(ctx, rank, world, iterations, cpu):
+    """UT iterations/s of the 400-run T-sweep: variants enumerated like JsonSubstitutions, w_list pinned to
+    default_rng(1000 + run index) (the reference's draw is unseeded, newcheb.py:905-909), runs split over the ranks by
+    batch.lpt_shards on nt x nb x nlevs x iteration budget, each rank ONE plan with its runs ordered by length,
+    ``iterations`` UT iterations (backward + forward sweep) in the throughput mode of the shipped report file
+    (plotting_flag tables_iter), final rows through batch.gather_results -- the only collective."""
+    import contextlib
+    import io
+    import torch
+    import torch.distributed as dist
+    from qcontrol_b200 import batch, config, control, newcheb, task_manager
+    t_setup = time.perf_counter()
+    variants = batch.expand_substitutions(ut_jx_template(iterations))
+    confs = []
+    for i, v in enumerate(variants):
+        with contextlib.redirect_stdout(io.StringIO()):
+            c = config.TaskRootConfiguration()
+            c.load(v)
+        batch.apply_auto_rules(c, i)
+        confs.append(c)
+    costs = [batch.estimate_cost(c) for c in confs]
+    shards = batch.lpt_shards(costs, world)
+    mine = sorted(shards[rank], key=lambda i: (-confs[i].fitter.propagation.nt, i))
+    pbs = []
+    for i in mine:
+        with contextlib.redirect_stdout(io.StringIO()):
+            tm = task_manager.create(confs[i])
+        pbs.append(newcheb.problem_from(confs[i], tm))
+    nb = control.NLevelBatch(pbs, ctx=ctx)
+    nb.time_sweeps, nb.sweep_ms = True, 0.0
+    ctx.synchronize()
+    setup_s = time.perf_counter() - t_setup
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    hist = nb.run_unit_transform(iter_max=iterations - 1, keep_fields=False)
+    ctx.synchronize()
+    wall = time.perf_counter() - t0
+    # steady state: iterations 1 .. n-1 from the loop's own time marks (iteration 0 carries the one-time host work:
+    # field tables of 3.2 M time points, first-touch of the host arrays); shipped runs do hundreds of iterations
+    marks = nb.iter_marks
+    steady = (marks[-1] - marks[1]) / max(iterations - 1, 1)
+    local = {i: np.array([h[-1].it, h[-1].goal_close, h[-1].Fsm, h[-1].E_int, h[-1].J]) for i, h in zip(mine, hist)}
+    t_g = time.perf_counter()
+    table = batch.gather_results(local, len(variants), 5)
+    gather_s = time.perf_counter() - t_g
+    assert not np.isnan(table).any() and np.all(table[:, 0] == iterations - 1)
+    steps_mine = sum(p.nt for p in pbs) * 2 * iterations * pbs[0].nb
+    stats = np.array([wall, nb.sweep_ms * 1e-3, float(steps_mine), float(sum(costs[i] for i in mine)), setup_s, gather_s,
+                      steady])
+    if world > 1:
+        t = torch.from_numpy(stats).cuda()
+        allr = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allr, t)
+        allr = np.stack([x.cpu().numpy() for x in allr])
+    else:
+        allr = stats[None]
+    nb.close()
+    if rank != 0:
+        return None
+    wall_max = float(allr[:, 0].max())
+    steady_max = float(allr[:, 6].max())
+    busy = allr[:, 1]
+    steps = float(allr[:, 2].sum())
+    nt_all = [c.fitter.propagation.nt for c in confs]
+    traj_bytes = sum(nt_all) * iterations * 2 * 2 * 2 * 16        # one slice written (bwd) + read (fwd): nb*nlevs*16 B
+    hbm_peak, hbm_src = hbm_peak_gbs()
+    out = {"workload": "input_batch/inp_Jx_250-19000fs_25runs.json: 400 runs, nt %d..%d, np=1, nch=8, nb=nlevs=2; "
+                       "w_list pinned; %d UT iterations each (fixed)" % (min(nt_all), max(nt_all), iterations),
+           "scaling": "strong (the 400 runs are split over the ranks by batch.lpt_shards)",
+           "ut_iterations_per_s": len(variants) / steady_max, "solver_steps_per_s": steps / iterations / steady_max,
+           "wall_s_per_iteration": steady_max,
+           "rate_basis": "iterations 1..%d of the call, from time marks inside the loop, slowest rank" % (iterations - 1),
+           "whole_call_wall_s": wall_max, "whole_call_ut_iterations_per_s": len(variants) * iterations / wall_max,
+           "per_rank_sweep_kernel_s": [float(b) for b in busy],
+           "imbalance_max_over_mean": float(busy.max() / busy.mean()),
+           "lpt_cost_max_over_mean": float(allr[:, 3].max() / allr[:, 3].mean()),
+           "runs_per_rank": [len(s) for s in shards], "setup_s_max": float(allr[:, 4].max()),
+           "gather_s_max": float(allr[:, 5].max()),
+           "hbm": {"algorithmic_bytes": traj_bytes, "achieved_gbs": traj_bytes / float(busy.max()) / 1e9,
+                   "peak_gbs": hbm_peak, "peak_source": hbm_src,
+                   "frac": traj_bytes / float(busy.max()) / 1e9 / hbm_peak},
+           "note": "latency-bound: a sweep lasts as long as the dependent chain of its longest run (nt = 9500 steps x "
+                   "~0.8 us), however few runs a rank holds, so splitting 400 runs over more GPUs does not shorten it; "
+                   "throughput grows with the number of runs per GPU instead (DESIGN.md, kernel B)"}
+    if cpu:
+        # CPU port beside it: one short run of the same batch (T = 0.25 ps, nt = 125), two iterations, one core
+        from oracle import qc_oracle as qo
+        user = dict(variants[0])
+        user["fitter"] = dict(user["fitter"], iter_max=1, w_list=list(confs[0].fitter.w_list))
+        pb = qo.make_problem(user, apply_auto=True)
+        t0 = time.perf_counter()
+        qo.Fitter(pb).run()
+        dt = time.perf_counter() - t0
+        sps = pb.nt * 2 * 2 * pb.nb / dt
+        cores = os.cpu_count() or 1
+        out["cpu_port"] = {"solver_steps_per_s_per_core": sps, "cores": cores,
+                           "ut_iterations_per_s_all_cores": cores * sps / (steps / (len(variants) * iterations)),
+                           "sample": "oracle.Fitter on run 0 (nt = %d), 2 iterations, 1 core; the all-core figure assumes "
+                                     "one run per core like the reference's SLURM farm (input_batch/runT-batch.sh)" % pb.nt}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# e2e_api: the call a user of the reference makes
+# ------------------------------------------------------------------------------------------------
+def e2e_api_block(rank, world, local_dev, runs, nt):
+    """newcheb.run_variants (the body of ``python newcheb.py --json_task ... --json_rep ...``, newcheb.py:641-975) on a
+    "@SUBST:LIST" template of ``runs`` two-level Krotov variants at np = 2048 (amplitude x pulse centre), from JSON
+    dictionaries to the gathered final rows: wall clock INCLUDING configuration, task_manager.create, Newton tables,
+    exp_L / field tables, plan upload, the control loops (iteration 0 + 1 Krotov iteration) and the report files."""
+    import tempfile
+    import torch.distributed as dist
+    from qcontrol_b200 import batch, newcheb
+    dt = 350e-15 / 230000
+    T = dt * nt
+    n_e0 = int(round(math.sqrt(runs)))
+    n_t0 = (runs + n_e0 - 1) // n_e0
+    tpl = {"task_type": "optimal_control_krotov", "pot_type": "morse", "wf_type": "morse", "hamil_type": "ntriv",
+           "init_guess": "gauss", "init_guess_hf": "exp", "nb": 1, "nlevs": 2, "T": T, "L": 5.0, "np": NP_, "a": 1.0,
+           "De": 20000.0, "x0p": -0.17, "a_e": 1.0, "De_e": 10000.0, "Du": 20000.0,
+           "fitter": {"epsilon": 1e-8, "impulses_number": 1, "iter_max": 1, "h_lambda": 0.0066, "mod_log": 10 ** 9,
+                      "propagation": {"m": 0.5, "nch": NCH, "nt": nt,
+                                      "E0": {"@SUBST:LIST": [2861.6 * (0.8 + 0.4 * k / max(n_e0 - 1, 1)) for k in range(n_e0)]},
+                                      "t0": {"@SUBST:LIST": [T * (0.4 + 0.2 * k / max(n_t0 - 1, 1)) for k in range(n_t0)]},
+                                      "sigma": T / 6, "nu_L": 0.29297e15}}}
+    with tempfile.TemporaryDirectory() as tmp:
+        rep = {"fitter": {"out_path": os.path.join(tmp, "run_{input:$.fitter.propagation.E0}_{input:$.fitter.propagation.t0}"),
+                          "plotting_flag": "tables_iter", "table.imin": -1}}
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        variants = batch.expand_substitutions(tpl)
+        tm = {}
+        results = newcheb.run_variants(variants, rep, device=local_dev, verbose=False, timings=tm)
+        local = {i: np.array([rows[-1].it, rows[-1].goal_close, rows[-1].Fsm, rows[-1].E_int, rows[-1].J])
+                 for i, rows in results.items() if rows}
+        table = batch.gather_results(local, len(variants), 5)
+        wall = time.perf_counter() - t0
+    assert not np.isnan(table).any()
+    iters = int(table[0, 0]) + 1
+    sweeps = 2 * iters - 1                          # the backward sweep of the last iteration feeds nothing and is skipped
+    if world > 1:
+        import torch
+        t = torch.tensor([wall], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+    units = len(variants) * NP_ * nt * sweeps
+    return {"value": units / wall, "unit": UNIT, "wall_s": wall, "runs": len(variants), "np": NP_, "nt": nt,
+            "krotov_iterations": iters, "sweeps_per_run": sweeps,
+            "call": "batch.expand_substitutions + newcheb.run_variants + batch.gather_results (strong scaling over the ranks)",
+            "rank0_split_s": {k: (round(v, 4) if isinstance(v, float) else v) for k, v in tm.items()},
+            "setup_s": tm.get("config_s", 0.0) + tm.get("task_setup_s", 0.0) + tm.get("plan_setup_s", 0.0)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -251,9 +581,11 @@ def run_gpu_arm(a):
     e2e = {"value": world * B * NP_ * nt / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(world * hin.numel() * 16),
            "d2h_bytes_per_step": int(world * hout.numel() * 16),
            "call": "qc_propagate_host on every GPU at once: H2D psi (pinned) + %d prescribed-field steps + D2H psi, "
-                   "copies pipelined against the propagation in chunks of 592 runs; slowest rank" % nt}
+                   "copies pipelined against the propagation in chunks of 592 runs; slowest rank" % nt,
+           "work": "a prescribed-field sweep per call, not the Krotov iteration `value` times: no overlap / trajectory "
+                   "traffic in the kernel, every wavefunction over PCIe both ways"}
 
-    line = None
+    roof = cpu = None
     if rank == 0:
         # ---- roofline of the dominant kernel: forward Krotov sweep, timed alone with CUDA events -----
         durs = []
@@ -269,41 +601,59 @@ def run_gpu_arm(a):
         peak_nominal = 148 * 64 * 2 * 1.965e9 / 1e12
         peak_meas = ctx.fp64_peak_tflops()
         traffic = traffic_src = None
-        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_grid_sweep.json")
+        tpath = os.path.join(ROOT, "profiles", "traffic_grid_sweep.json")
         if os.path.exists(tpath):         # DRAM bytes of this kernel from the committed ncu capture, scaled per (run, step)
             with open(tpath) as f:
                 tj = json.load(f)
             traffic = tj["dram_bytes_per_run_step"] * B * nt
-            traffic_src = tj["source"]
+            traffic_src = tj["source"] + " -- a constant from that capture scaled by runs x nt, not measured in this run"
         roof = {"bound": "fp64", "achieved": achieved, "peak": peak_meas, "unit": "TFLOP/s", "frac": achieved / peak_meas,
-                "traffic": traffic, "traffic_source": traffic_src, "peak_source": "measured here: qc_measure_fp64_peak (DFMA chains, burst); MEASURED_PEAKS.json has no FP64 entry",
-                "peak_nominal": peak_nominal, "kernel": "grid_sweep_kernel<11> (Krotov forward sweep)",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": "measured here: qc_measure_fp64_peak (DFMA chains, burst); MEASURED_PEAKS.json has no FP64 entry",
+                "peak_nominal": peak_nominal, "frac_of_nominal": achieved / peak_nominal,
+                "kernel": "grid_sweep_kernel<11, VAR=1> (Krotov forward sweep, phi hand-over through tensor memory)",
                 "kernel_ms_per_launch": kdur * 1e3, "flops_per_launch": flops_launch,
                 "hbm_algorithmic_bytes_per_launch": (32 * NP_ + 16) * B * nt,
                 "hbm_gbs_achieved": (32 * NP_ + 16) * B * nt / kdur / 1e9}
-        # ---- CPU baseline beside it ---------------------------------------------------------------------
-        cpu = None
+    gb.close()
+
+    # ---- the reference's own batch on kernel B (BASELINE config 4), sharded over the ranks -----------------------
+    extra = {}
+    if not a.no_extra:
+        ut = ut_jx_tsweep_block(ctx, rank, world, a.ut_iterations, cpu=not a.no_cpu)
+        if rank == 0:
+            extra["ut_jx_tsweep"] = ut
+    ctx.close()
+    e2e_api = None
+    if not a.no_extra:
+        e2e_api = e2e_api_block(rank, world, local, a.api_runs, a.api_nt)
+        if rank == 0:
+            e2e_api["vs_value"] = e2e_api["value"] / value
+
+    if rank == 0:
+        # ---- CPU baseline beside it (rank 0, bounded sample) ----------------------------------------------------------
         if not a.no_cpu:
             cores = os.cpu_count() or 1
-            v, wall = cpu_rate(a.cpu_steps, cores)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "%d processes x 1 run x %d time steps of the same workload (np=%d, nch=%d); %.1f s wall" % (
-                       cores, a.cpu_steps, NP_, NCH, wall)}
+            kind = cpu_kind()
+            farm = CpuFarm(kind, cores, 2 * a.cpu_steps + 2)
+            try:
+                farm.run(max(2, a.cpu_steps // 8))
+                secs = farm.run(a.cpu_steps)
+            finally:
+                farm.close()
+            cpu = {"value": cores * NP_ * a.cpu_steps / secs, "unit": UNIT, "cores": cores, "kind": kind,
+                   "sample": cpu_sample_text(kind, cores, a.cpu_steps) + "; %.1f s" % secs}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "krotov_batch_8192x2048", "runs_per_gpu": B, "np": NP_, "nlevs": NLEVS, "nch": NCH,
-                           "nt": nt, "step": "one Krotov iteration (forward + backward sweep) of every run",
-                           "l2": "working set (trajectories + state, %.1f GB) exceeds L2" % (
-                               (2 * (nt + 1) * B * NP_ * 16 + 3 * B * 2 * NP_ * 16) / 1e9)},
-                "krotov_iterations_per_s": iters_per_s, "gpu_launches": int(launches), "clocks": sampler.summary(),
-                "roofline": roof, "e2e": e2e, "cpu_baseline": cpu}
+                "dtype": "f64", "data": "synthetic", "config": bench_config(a),
+                "krotov_iterations_per_s": iters_per_s,
+                "krotov_iterations_note": "iterations of %d-step sweeps (nt = %d per sweep)" % (nt, nt),
+                "gpu_launches": int(launches), "clocks": sampler.summary(),
+                "roofline": roof, "e2e": e2e, "e2e_api": e2e_api, "cpu_baseline": cpu, "extra": extra}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    gb.close()
-    ctx.close()
 
 
 def main():
@@ -317,11 +667,28 @@ def main():
     ap.add_argument("--nt", type=int, default=16, help="time steps per sweep")
     ap.add_argument("--cpu-steps", type=int, default=96, help="time steps each host process propagates for the CPU figure")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the ut_jx_tsweep and e2e_api blocks")
+    ap.add_argument("--ut-iterations", type=int, default=10)
+    ap.add_argument("--api-runs", type=int, default=1024)
+    ap.add_argument("--api-nt", type=int, default=1024)
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference_arm(a)
-    else:
-        run_gpu_arm(a)
+        return
+    world = os.environ.get("WORLD_SIZE")
+    if world is None and a.gpus > 1:
+        # launched without torchrun: start one rank per GPU exactly as the bench contract describes
+        import socket
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        os.execv(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(a.gpus),
+                                  "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)]
+                 + sys.argv[1:])
+    if world is not None and int(world) != a.gpus:
+        sys.exit("bench.py: --gpus %d but WORLD_SIZE=%s: launch one rank per GPU (torchrun --nproc-per-node %d)"
+                 % (a.gpus, world, a.gpus))
+    run_gpu_arm(a)
 
 
 if __name__ == "__main__":

@@ -136,7 +136,9 @@ int32_t qc_get_state(qc_plan *plan, double *psi);
  * b = batched ? batch : 1. */
 int32_t qc_set_step_scalars(qc_plan *plan, int32_t which, const double *vals, int32_t batched);
 
-/* Per-run control scalars: ctl[batched ? batch : 1][4] = (h_lambda, nt, reserved, reserved);
+/* Per-run control scalars: ctl[batched ? batch : 1][4] = (h_lambda, nt, retired, reserved);
+ * retired != 0 (N-level plans): the run takes no further part in sweeps -- the control loop of a batch keeps
+ * iterating the runs that have not converged yet (fitter.py:545-546) while finished ones keep their slot;
  * a0[batch][nb] complex = aF_type(...) (task_manager.py:209-268), may be NULL. */
 int32_t qc_set_control(qc_plan *plan, const double *ctl, int32_t batched, const double *a0);
 

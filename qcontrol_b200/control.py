@@ -142,10 +142,11 @@ def _shown_fields(Et):
     return np.where(Et.imag != 0.0, np.abs(Et), Et.real)
 
 
-def field_integral(Et, t_step):
-    """E_int = sum_{l>=1} |E_l|^2 * dt[fs] (fitter.py:338-341)."""
+def field_integral(Et, t_step, exact=True):
+    """E_int = sum_{l>=1} |E_l|^2 * dt[fs] (fitter.py:338-341).  exact: the reference's scalar accumulation order
+    (bit-identical E_int); big batches pass exact=False and get the same sum from one numpy reduction."""
     Et = np.asarray(Et)
-    if Et.shape[0] <= 4096:
+    if exact and Et.shape[0] <= 4096:
         acc = np.float64(0.0)
         for k in range(1, Et.shape[0]):
             acc += Et[k] * Et[k].conjugate() * (t_step * 1e15)
@@ -249,17 +250,50 @@ class GridBatch(_BatchBase):
         for p in self.pbs:
             assert np.array_equal(p.akx2, p0.akx2), "one kinetic multiplier per batch"
         if p0.hf_hide:
+            # exp_L[l] = csqrt(hf(t_l)) with the reference's scalar expressions (branch cut of cmath.sqrt).
+            # The table depends on the time grid and the carrier only, which most runs of a batch share (the
+            # variants of a template differ in a scalar or two): one evaluation per distinct (grid, carrier)
             for slot, d in ((0, FORWARD), (1, BACKWARD)):
-                rows = []
+                rows, seen = [], {}
                 for p in self.pbs:
-                    ts = step_times(p, d)
-                    rows.append([np.complex128(cmath.sqrt(p.laser_field_hf(np.float64(1.0), t, p.pcos, p.w_list)))
-                                 for t in ts])
+                    key = None
+                    if getattr(p, "carrier", None) and getattr(p, "nu", None) is not None:
+                        key = (p.carrier, float(p.nu), float(p.T), float(p.t_step), int(p.nt), float(p.pcos),
+                               tuple(float(w) for w in p.w_list))
+                    if key is None or key not in seen:
+                        row = [np.complex128(cmath.sqrt(p.laser_field_hf(np.float64(1.0), t, p.pcos, p.w_list)))
+                               for t in step_times(p, d)]
+                        if key is not None:
+                            seen[key] = row
+                    else:
+                        row = seen[key]
+                    rows.append(row)
                 self.plan.set_exp_L(self._pad(rows), slot)
         self.plan.set_control(np.array([float(p.h_lambda) for p in self.pbs]), self.nt.astype(np.float64))
 
+    def _vectorised(self):
+        """Big batches evaluate their per-step tables with numpy over the whole time grid instead of the reference's
+        scalar expressions (last-ulp differences in libm calls; every parity test is below the threshold)."""
+        return int(self.nt.sum()) > VECTOR_SETUP_POINTS
+
     def _prescribed_field(self, p, direction):
         """LaserFieldEnvelope / ...Backward for tasks without feedback (fitter.py:650-670, 809)."""
+        key = (id(p), direction)
+        cache = self.__dict__.setdefault("_presc_cache", {})
+        if key not in cache:
+            cache[key] = self._prescribed_field_eval(p, direction)
+        return cache[key]
+
+    def _prescribed_field_eval(self, p, direction):
+        if self._vectorised() and getattr(p, "envelope", None) and getattr(p, "carrier", None):
+            t = np.array(step_times(p, direction), np.float64)
+            E = np.asarray(_env_vec(p.envelope, p.E0, t, p.t0, p.sigma), np.float64)
+            if not (direction == BACKWARD or p.hf_hide):
+                E = E * _hf_vec(p.carrier, p.nu, t, p.pcos, p.w_list)
+            if direction == FORWARD and p.task_type == "intuitive_control":
+                for k in range(1, p.impulses_number):
+                    E = E + _env_vec(p.envelope, p.E0, t, p.t0 + k * p.delay, p.sigma)
+            return list(E)
         out = []
         for t in step_times(p, direction):
             if direction == BACKWARD or p.hf_hide:
@@ -299,9 +333,11 @@ class GridBatch(_BatchBase):
             E = E.real.astype(np.complex128)
         gc = pl.goal_overlap(1)
         rows = []
+        exact = not self._vectorised()
         for b, p in enumerate(self.pbs):
-            Et = np.array([E0_start[b]] + [E[b, l] for l in range(1, p.nt + 1)])
-            E_int = field_integral(Et, p.t_step)
+            Et = E[b, :p.nt + 1].copy()
+            Et[0] = E0_start[b]
+            E_int = field_integral(Et, p.t_step, exact)
             F = _F_value(p.F_type, gc[b], p.nb)
             hl = p.h_lambda if p.task_type == "optimal_control_krotov" else np.float64(0.0)
             J = F.real - hl * hl * E_int.real
@@ -508,12 +544,14 @@ class NLevelBatch(_BatchBase):
             sc += gc0[v]
         F0 = _F_value(p.F_type, gc0, p.nb)
         if self._vectorised() and getattr(p, "envelope", None):
-            t = np.array(p.t_list, np.float64)
-            El = list((_env_vec(p.envelope, p.E0, t, p.t0, p.sigma) * _hf_vec(p.carrier, p.nu, t, p.pcos, p.w_list)).real)
+            t = np.asarray(p.t_list, np.float64)
+            El = np.ascontiguousarray((_env_vec(p.envelope, p.E0, t, p.t0, p.sigma) *
+                                       _hf_vec(p.carrier, p.nu, t, p.pcos, p.w_list)).real)
+            Ei = field_integral(El, p.t_step, exact=False).real
         else:
             El = [(p.laser_field(p.E0, t, p.t0, p.sigma) * p.laser_field_hf(np.float64(1.0), t, p.pcos, p.w_list)).real
                   for t in p.t_list]
-        Ei = field_integral(np.array([0.0] + list(El[1:])), p.t_step).real
+            Ei = field_integral(np.array([0.0] + list(El[1:])), p.t_step).real
         h0 = p.h_lambda * RED_PLANCK_H / CM_TO_ERG if p.ntriv == -1 else p.h_lambda
         return IterRow(-1, float(abs(sc)), float(F0.real), float(Ei), float(F0.real - h0 * h0 * Ei), np.array(El))
 
@@ -570,6 +608,8 @@ class NLevelBatch(_BatchBase):
             # ---- backward sweep from the goal basis (fitter.py:241-249) ----------------------------
             pl.snapshot_load(1)
             pl.record_state(1, 0)
+            if it > 0:                                    # finished runs leave the sweeps (their warps retire at once)
+                pl.set_control(h_lambda, self.nt.astype(np.float64), retired=done)
             if it == 0:
                 pl.set_control(1.0, self.nt.astype(np.float64))
                 pl.set_E_base(self._pad(self._field_rows(BACKWARD)))
@@ -593,7 +633,7 @@ class NLevelBatch(_BatchBase):
                 dyn = mode_dyn & (goal_close_abs != 0.0)
                 h_lambda = np.where(dyn, h0_all * nb_runs / np.sqrt(np.where(dyn, goal_close_abs, 1.0)), h0_all)
                 a0 = a_batch(kind, self.psi0, chi_init, self.dx)
-            pl.set_control(h_lambda, self.nt.astype(np.float64), a0)
+            pl.set_control(h_lambda, self.nt.astype(np.float64), a0, retired=done)
             if it == 0:
                 pl.set_E_base(self._pad(base_rows))
             pl.snapshot_load(0)

@@ -877,7 +877,15 @@ static int32_t run_sweep(qc_plan *pl, const qc_sweep_args *a, bool single_step, 
         switch (pl->log2n) {
             case 8: return launch_grid<8>(pl, g, lst);
             case 9: return launch_grid<9>(pl, g, lst);
-            case 10: return launch_grid<10>(pl, g, lst);
+            case 10:
+                // two runs per CTA with the tensor-memory hand-over once the batch fills every SM anyway (the plain
+                // form holds two one-run CTAs per SM: same residency, 20 % more shared-memory traffic)
+                {
+                    bool two = var == 1 && g.run_count > pl->ctx->sm_count;
+                    if (const char *e = getenv("QC_GRID_TMP")) two = atoi(e) != 0;      // tests force either form
+                    if (two) return launch_grid<10, false, false, 2, false, 1>(pl, g, lst);
+                }
+                return launch_grid<10>(pl, g, lst);
             case 11:
                 if (var == 1) return launch_grid<11, false, false, 0, false, 1>(pl, g, lst);
                 return launch_grid<11>(pl, g, lst);

@@ -95,6 +95,8 @@ struct GridParams {
 // freed columns hold the second phi buffer of each level, so the partner reads this level's phi of either order parity
 // straight from the lane with tcgen05.ld.  Shared memory then carries nothing but the four FFT transposes per order:
 // 10 -> 8 complex128 accesses per point and order (-20 % of the busiest pipe), 200 KB -> 68 KB per CTA.
+// With RPC = 128 / TPL runs per CTA (np = 1024: two runs) the same pairing holds for smaller grids: run r owns lane
+// quadrants r * WPL .. (r + 1) * WPL - 1 (WPL = TPL / 32 warps per level), level 0 in warps 0-3, level 1 in warps 4-7.
 template <int LOG2N, bool CL = false, int RPC = 0, bool ILV = false, int VAR = 0>
 struct GridCfg {
     static constexpr int N = 1 << LOG2N;
@@ -110,7 +112,8 @@ struct GridCfg {
     static constexpr int MAXCH = 128;
     static constexpr bool NAMED = !CL && !PK && TPL >= 32;   // a level is made of whole warps: per-level named barriers
     static constexpr bool TMH = (VAR & 1) != 0;              // phi hand-over through tensor memory
-    static_assert(!TMH || (!CL && !PK && TPL == 128), "tensor-memory hand-over: levels must be warps w and w + 4");
+    static_assert(!TMH || (!CL && !ILV && (PK ? RPC * TPL == 128 : TPL == 128)),
+                  "tensor-memory hand-over: thread t of the two levels must sit in warps w and w + 4");
     static constexpr int TM_COLS = NTHREADS > 128 ? 512 : 256;   // 256 TMEM columns per warp slot
     // shared memory (complex elements): per level ONE transpose buffer (forward and inverse passes use it in turn:
     // every element is either private to an R3-lane group or read by the thread that wrote it, except across the two
@@ -293,8 +296,8 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
     static_assert(!(LOCAL && CL), "local control runs in the single-CTA form");
     static_assert(!(RPC > 0 && (LOCAL || CL)), "the packed form exists for the plain single-CTA kernel only");
     static_assert(!ILV || RPC > 0, "interleaved levels are a layout of the packed form");
-    static_assert(ILV || RPC == 0 || GridCfg<LOG2N>::TPL == 32, "packed level-per-warp layout: a level is one warp");
     typedef GridCfg<LOG2N, CL, RPC, ILV, VAR> C;
+    static_assert(ILV || RPC == 0 || C::TMH || GridCfg<LOG2N>::TPL == 32, "packed level-per-warp layout: a level is one warp");
     static_assert(!(C::TMH && LOCAL), "local control keeps the shared-memory hand-over (it reuses the buffers)");
     constexpr bool TMH = C::TMH;
     constexpr int N = C::N, TPL = C::TPL, R3 = C::R3, Q = C::Q, S1 = C::S1, BUF = C::BUF;
@@ -308,8 +311,12 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
     // packed form: run slot rslot of this CTA, thread rtid of the run.  ILV: the two levels of grid point set t sit
     // in lanes L and L^16 of one warp, so the coupling term is a warp shuffle (in k space, where both levels hold
     // the same frequencies) instead of a shared-memory hand-over.  A run synchronises on named barriers of its own
-    const int rslot = PK ? tid / C::RT : 0;
-    const int rtid = PK ? tid - rslot * C::RT : tid;
+    // TMP (tensor-memory hand-over with several runs per CTA): level 0 of every run in warps 0-3, level 1 in warps 4-7,
+    // run r in the lane quadrants r * WPL ..; rtid is the thread's index inside its run, level 0 first, as elsewhere
+    constexpr bool TMP = TMH && PK;
+    constexpr int WPL = TPL >= 32 ? TPL / 32 : 1;      // warps per level
+    const int rslot = !PK ? 0 : TMP ? ((tid >> 5) & 3) / WPL : tid / C::RT;
+    const int rtid = !PK ? tid : TMP ? (tid >> 7) * TPL + (((tid >> 5) & 3) % WPL) * 32 + (tid & 31) : tid - rslot * C::RT;
     cd *sm = reinterpret_cast<cd *>(smem_raw + (PK ? rslot * C::RUN_BYTES : 0));
     const int lev = CL ? (int)cooperative_groups::this_cluster().block_rank() : ILV ? (rtid >> 4) & 1 : rtid / TPL;
     const int t = CL ? tid : ILV ? (rtid & 15) | ((rtid >> 5) << 4) : rtid - lev * TPL;
@@ -332,7 +339,8 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
     if (!PK && !valid) return;
     const int run = valid ? p.run_first + slot : p.run_first;
     auto level_sync = [&]() {                     // all threads of this thread's level (packed form: of the run)
-        if (PKL) __syncwarp();
+        if (TMP && WPL > 1) bar_sync(1 + 7 * rslot + lev, TPL);
+        else if (PKL) __syncwarp();
         else if (PK) {
             if (RW == 1) __syncwarp(); else bar_sync(1 + rslot, C::RT);
         } else if (NAMED) bar_sync(1 + lev, TPL); else __syncthreads();
@@ -341,8 +349,9 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
     // Packed form: interleaved layout one id per run (1 + rslot); level-per-warp layout five per run (four "available"
     // ids and one for sums).  A "phi has been read" handshake is not needed: the buffers alternate with the order
     // parity, and a level passes its wait for the partner's order j+1 only after the partner has finished order j.
-    const int bar_run = PKL ? 1 + 5 * rslot + 4 : 1 + rslot;
-    const int bar_full = PKL ? 1 + 5 * rslot : 3;
+    // TMP: seven per run (two level barriers, four "available" ids, one for sums).
+    const int bar_run = TMP ? 1 + 7 * rslot + 6 : PKL ? 1 + 5 * rslot + 4 : 1 + rslot;
+    const int bar_full = TMP ? 1 + 7 * rslot + 2 : PKL ? 1 + 5 * rslot : 3;
     auto both_sums = [&](double val, double &s0, double &s1) {
         if (CL) cluster_sums<C::NTHREADS>(val, s_red, tid, lev, s0, s1);
         else if (PKL) packed_level_sums<RW>(val, s_red, rtid, bar_run, s0, s1);

@@ -73,8 +73,18 @@ __global__ void __launch_bounds__(128) nlevel_sweep_kernel(NLevelParams p) {
     const double c2 = 2.0 * (emax + emin) / (emax - emin);
     const double dx = p.dx[(long long)p.dx_stride * run];
     const double h_lambda = p.ctl[(long long)p.ctl_stride * run * 4 + 0];
-    const int nt = (int)p.ctl[(long long)p.ctl_stride * run * 4 + 1];
+    // ctl[run] = (h_lambda, nt, retired, -): a retired run (converged, diverged or stopped in an earlier iteration of
+    // the control loop) keeps its slot in the plan but does no step and no store
+    const bool retired = p.ctl[(long long)p.ctl_stride * run * 4 + 2] != 0.0;
+    const int nt = retired ? -1 : (int)p.ctl[(long long)p.ctl_stride * run * 4 + 1];
     const double inv_h_lambda = 1.0 / h_lambda;
+    // A warp leaves the time loop with its longest live run (the basis vectors of a run never straddle warps, so the
+    // shuffles below stay convergent).  With the runs of a plan ordered by length (control.NLevelBatch) a launch
+    // keeps only the warps of the runs that are still propagating, and its tail costs nothing.
+    int warp_last = (in_range && !retired) ? nt : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
+    const int l_end = p.single_step ? p.l_first + p.nsteps : min(p.l_first + p.nsteps, warp_last + 1);
     const double U = p.uwd ? p.uwd[(long long)p.uwd_stride * run * 3 + 0] : 0.0;
     const double W = p.uwd ? p.uwd[(long long)p.uwd_stride * run * 3 + 1] : 0.0;
     const double delta = p.uwd ? p.uwd[(long long)p.uwd_stride * run * 3 + 2] : 0.0;
@@ -154,7 +164,7 @@ __global__ void __launch_bounds__(128) nlevel_sweep_kernel(NLevelParams p) {
     StepIn nxt = fetch(p.l_first);
     const cd E_single = p.single_step ? p.E_step[run] : cmk(0.0, 0.0);
 
-    for (int l = p.l_first; l < p.l_first + p.nsteps; ++l) {
+    for (int l = p.l_first; l < l_end; ++l) {
         const bool live = active && l <= nt;
         const StepIn cur = nxt;
         // ---- field -------------------------------------------------------------
@@ -263,7 +273,7 @@ __global__ void __launch_bounds__(128) nlevel_sweep_kernel(NLevelParams p) {
             }
         }
     }
-    if (active) {
+    if (active && !retired) {
 #pragma unroll
         for (int n = 0; n < NL; ++n) p.psi[((long long)run * p.nb + vec) * NL + n] = psi[n];
     }

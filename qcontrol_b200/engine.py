@@ -175,13 +175,19 @@ class Plan:
     def set_s_env(self, s):
         self._set_scalars(2, s)
 
-    def set_control(self, h_lambda, nt, a0=None):
+    def set_control(self, h_lambda, nt, a0=None, retired=None):
+        """Per-run control scalars (h_lambda, nt) and, for N-level plans, the 'a' coefficients; ``retired[batch]``
+        marks runs that take no further part in sweeps (converged / stopped runs of a batch keep their slot)."""
         h = np.atleast_1d(np.asarray(h_lambda, np.float64))
         n = np.atleast_1d(np.asarray(nt, np.float64))
         rows = max(h.shape[0], n.shape[0])
+        if retired is not None:
+            rows = self.batch
         assert rows in (1, self.batch)
         ctl = np.zeros((rows, 4), np.float64)
         ctl[:, 0], ctl[:, 1] = h, n
+        if retired is not None:
+            ctl[:, 2] = np.asarray(retired, np.float64)
         a = _c128(a0, (self.batch, self.nb)) if a0 is not None else None
         check(lib.qc_set_control(self._h, _ptr(ctl), int(rows == self.batch and self.batch > 1),
                                  _ptr(a.view(np.float64)) if a is not None else None))

@@ -143,7 +143,9 @@ def memory_chunks(confs, idxs, free_bytes, fraction=0.8):
     trajectory buffers of a Krotov / UT plan live in HBM: 2 * (nt + 1) * np * 16 B per run on the grid (7.5 GB for
     the shipped Krotov input), so one plan per shape group does not fit arbitrary batches.  Runs are taken longest
     first, so that a sub-batch holds runs of similar length (the plan is sized by its longest run), and a sub-batch
-    is closed when qc_plan_footprint of one more run would exceed ``fraction`` of the free bytes."""
+    is closed when qc_plan_footprint of one more run would exceed ``fraction`` of the free bytes.  Inside a sub-batch
+    the runs stay ordered by length: neighbouring runs share warps / SMs, so the warps of the short runs of a ragged
+    batch retire together (kernel B) instead of idling beside a long run."""
     if not idxs:
         return []
     c0 = confs[idxs[0]]
@@ -161,7 +163,7 @@ def memory_chunks(confs, idxs, free_bytes, fraction=0.8):
     for i in order:
         nt_max = int(confs[(cur or [i])[0]].fitter.propagation.nt)
         if cur and not fits(len(cur) + 1, nt_max):
-            chunks.append(sorted(cur))
+            chunks.append(cur)
             cur = []
             nt_max = int(confs[i].fitter.propagation.nt)
         if not cur and not fits(1, nt_max):
@@ -169,7 +171,7 @@ def memory_chunks(confs, idxs, free_bytes, fraction=0.8):
                               % (i, nt_max, c0.np, 100 * fraction, free_bytes / 1e9))
         cur.append(i)
     if cur:
-        chunks.append(sorted(cur))
+        chunks.append(cur)
     return chunks
 
 

@@ -64,6 +64,8 @@ class RunProblem:
     delay: float = 0.0
     F_type: str = "sm"
     F_goal: float = -1.0
+    envelope: str = "gauss"
+    carrier: str = "exp"
 
     def laser_field(self, E0, t, t0, sigma):            # gaussian envelope, task_manager.py:27-40
         return E0 * math.exp(-(t - t0) * (t - t0) / 2.0 / sigma / sigma)

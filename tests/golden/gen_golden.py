@@ -32,28 +32,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def load_reference():
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
-    shim = re.compile(r"(\w+)\.itemset\(\((.+?),\s*(.+?)\),\s*(.+)\)\s*(#.*)?$", re.M)
-
-    def load_shimmed(name):
-        src = open(os.path.join(REF, name + ".py")).read()
-        src = shim.sub(lambda m: "%s[%s, %s] = %s" % (m.group(1), m.group(2), m.group(3), m.group(4)), src)
-        assert "itemset" not in src, name
-        mod = types.ModuleType(name)
-        mod.__file__ = os.path.join(REF, name + ".py")
-        sys.modules[name] = mod
-        exec(compile(src, mod.__file__, "exec"), mod.__dict__)
-        return mod
-
-    import math_base, phys_base, psi_basis  # noqa: F401
-    load_shimmed("hamil_2d")
-    import propagation  # noqa: F401
-    load_shimmed("task_manager")
-    import fitter, config, reporter  # noqa: F401
-    return types.SimpleNamespace(**{k: sys.modules[k] for k in
-                                    ("math_base", "phys_base", "psi_basis", "hamil_2d", "propagation",
-                                     "task_manager", "fitter", "config", "reporter")})
+    """The unmodified reference modules, imported from where they lie (oracle/ref_loader.py holds the shim)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle.ref_loader import load_reference as _load
+    return _load(REF)
 
 
 def load_table(name):

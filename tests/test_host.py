@@ -175,7 +175,7 @@ def test_memory_sized_sub_batches_host_logic():
     chunks = newcheb.memory_chunks(confs, list(range(6)), free_bytes=two / 0.8 + 1, fraction=0.8)
     assert sorted(i for c in chunks for i in c) == list(range(6))
     assert chunks[0] == [1, 3] and all(len(c) <= 3 for c in chunks) and len(chunks) >= 3
-    assert newcheb.memory_chunks(confs, list(range(6)), free_bytes=1e12) == [list(range(6))]
+    assert newcheb.memory_chunks(confs, list(range(6)), free_bytes=1e12) == [[1, 3, 5, 2, 0, 4]]      # longest first
     with pytest.raises(MemoryError):
         newcheb.memory_chunks(confs, [1], free_bytes=one / 2)
     shipped = engine.plan_footprint(engine.HAMIL_NONTRIV, 1024, 2, 1, 64, 1, 230000, True, True)
