@@ -124,6 +124,14 @@ int32_t qc_set_static(qc_plan *plan, const double *v, int32_t v_batched, const d
 int32_t qc_set_poly(qc_plan *plan, int32_t slot, const double *xp, const double *dv, const double *sc,
                     int32_t batched);
 
+/* OPT-IN truncation of the interpolation series: orders[batched ? batch : 1] = number of terms dv_0 .. dv_{J-1}
+ * actually summed by sweeps with this slot (2 <= J <= nch); NULL restores the full series.  The reference always sums
+ * all nch terms (phys_base.py:165), although math_base.points leaves divided differences of round-off size (~1e-17)
+ * behind the converged part; the host chooses J from a rigorous bound on the dropped tail
+ * (qcontrol_b200.math_base.truncation_order).  Off unless called: results then differ from the reference's by that
+ * bound per step instead of by round-off. */
+int32_t qc_set_poly_orders(qc_plan *plan, int32_t slot, const int32_t *orders, int32_t batched);
+
 /* State psi[batch][nb][nlevs][np] complex: DynamicState.psi (propagation.py:55-71). */
 int32_t qc_set_state(qc_plan *plan, const double *psi);
 int32_t qc_get_state(qc_plan *plan, double *psi);

@@ -18,7 +18,7 @@ SYMBOLS = (
     "qc_abi_version", "qc_last_error", "qc_create", "qc_destroy", "qc_synchronize", "qc_timer_start",
     "qc_timer_stop", "qc_launch_count", "qc_measure_fp64_peak", "qc_mem_info", "qc_plan_create", "qc_plan_destroy",
     "qc_plan_footprint",
-    "qc_set_static", "qc_set_poly", "qc_set_state", "qc_get_state", "qc_set_step_scalars", "qc_set_control",
+    "qc_set_static", "qc_set_poly", "qc_set_poly_orders", "qc_set_state", "qc_get_state", "qc_set_step_scalars", "qc_set_control",
     "qc_sweep", "qc_prop_step", "qc_apply_hamil", "qc_set_instr_grid", "qc_instrument", "qc_set_local_control", "qc_get_local_state", "qc_set_local_state", "qc_get_fields", "qc_field_integral", "qc_get_norms", "qc_snapshot_set", "qc_snapshot_load", "qc_goal_overlap", "qc_krotov_terminal",
     "qc_get_traj", "qc_record_state", "qc_propagate_host",
     "qc_plan2d_create", "qc_plan2d_destroy", "qc_plan2d_set_static", "qc_plan2d_set_poly", "qc_plan2d_set_state",
@@ -68,6 +68,7 @@ def _load():
         "qc_plan_destroy": (i32, [vp]),
         "qc_set_static": (i32, [vp, dp, i32, dp, dp, i32, dp, i32]),
         "qc_set_poly": (i32, [vp, i32, dp, dp, dp, i32]),
+        "qc_set_poly_orders": (i32, [vp, i32, C.POINTER(C.c_int32), i32]),
         "qc_set_state": (i32, [vp, dp]),
         "qc_get_state": (i32, [vp, dp]),
         "qc_set_step_scalars": (i32, [vp, i32, dp, i32]),

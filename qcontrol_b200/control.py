@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import cmath
 import math
+import os
 import time
 from dataclasses import dataclass
 from typing import List, Sequence
@@ -158,7 +159,7 @@ TRAJ_TASKS = ("optimal_control_krotov", "optimal_control_unit_transform")
 
 
 class _BatchBase:
-    def __init__(self, problems: Sequence, ctx: eng.Context = None, device: int = 0, store_traj=None):
+    def __init__(self, problems: Sequence, ctx: eng.Context = None, device: int = 0, store_traj=None, poly_tol=None):
         """store_traj: allocate the two trajectory buffers [batch][nt_max+1][np] (grid) -- None = only for the task
         types whose field update reads the previous opposite sweep (Krotov, unitary transformation); pass True to
         record a prescribed-field sweep with ``propagate(record=True)``.  A filtering run of the shipped length
@@ -167,6 +168,10 @@ class _BatchBase:
         p0 = self.pbs[0]
         if store_traj is None:
             store_traj = getattr(p0, "task_type", "") in TRAJ_TASKS
+        # opt-in truncation of the interpolation series (qc_set_poly_orders): a per-step error bound, e.g. 1e-11
+        if poly_tol is None and os.environ.get("QC_POLY_TOL"):
+            poly_tol = float(os.environ["QC_POLY_TOL"])
+        self.poly_tol = poly_tol
         self.B = len(self.pbs)
         self.ctx = ctx or eng.Context(device)
         for p in self.pbs:
@@ -199,6 +204,10 @@ class _BatchBase:
             xp, dvs = tabs[0][0], np.stack([t[1] for t in tabs])
         self.plan.set_poly(slot, xp, dvs, np.array(emins), np.array(emaxs), np.array(tscs), np.array(eLs))
         self._poly_dir[direction] = slot
+        if self.poly_tol:
+            self.poly_orders = getattr(self, "poly_orders", {})
+            self.poly_orders[direction] = math_base.truncation_order(nch, dvs, self.poly_tol)
+            self.plan.set_poly_orders(slot, self.poly_orders[direction])
 
     time_sweeps = False  # accumulate CUDA-event time of the sweep launches in sweep_ms (synchronises)
     sweep_ms = 0.0

@@ -89,8 +89,9 @@ struct DevBuf {
 struct PolySlot {
     DevBuf<double> xp, sc;
     DevBuf<cd> dv;
+    DevBuf<int> orders;      // optional: polynomial terms actually summed per run (qc_set_poly_orders), else nch
     int batched = 0;
-    bool set = false;
+    bool set = false, truncated = false;
 };
 
 struct qc_plan {
@@ -622,7 +623,7 @@ extern "C" int32_t qc_plan_destroy(qc_plan *pl) {
     pl->a0.release(); pl->E_step.release(); pl->tw1.release(); pl->tw2.release(); pl->goal.release();
     pl->gc.release(); pl->tmp_row.release(); for (auto &b : pl->snap) b.release(); pl->traj[0].release(); pl->traj[1].release();
     pl->v.release(); pl->kin.release(); pl->uwd.release(); pl->dx.release(); pl->ctl.release(); pl->norms.release();
-    for (auto &s : pl->poly) { s.xp.release(); s.sc.release(); s.dv.release(); }
+    for (auto &s : pl->poly) { s.xp.release(); s.sc.release(); s.dv.release(); s.orders.release(); }
     for (auto &b : pl->work) b.release();
     pl->zero_v.release(); pl->akx.release(); pl->xgrid.release(); pl->instr.release();
     pl->lc.release(); pl->lc_t.release(); pl->lc_rt.release(); pl->lc_rdiag.release();
@@ -672,6 +673,27 @@ extern "C" int32_t qc_set_poly(qc_plan *pl, int32_t slot, const double *xp, cons
     if (rc) return rc;
     s.batched = batched ? 1 : 0;
     s.set = true;
+    return QC_OK;
+}
+
+extern "C" int32_t qc_set_poly_orders(qc_plan *pl, int32_t slot, const int32_t *orders, int32_t batched) {
+    if (!pl) return fail(QC_ERR_ARG, "qc_set_poly_orders: NULL plan");
+    if (slot < 0 || slot > 1 || !pl->poly[slot].set) return fail(QC_ERR_STATE, "qc_set_poly_orders: slot %d has no polynomial yet", slot);
+    PolySlot &s = pl->poly[slot];
+    if (!orders) {
+        s.truncated = false;
+        return QC_OK;
+    }
+    if ((batched != 0) != (s.batched != 0)) return fail(QC_ERR_ARG, "qc_set_poly_orders: batched must match qc_set_poly");
+    QC_CUDA(cudaSetDevice(pl->ctx->device));
+    const size_t rows = batched ? pl->d.batch : 1;
+    for (size_t r = 0; r < rows; ++r)
+        if (orders[r] < 2 || orders[r] > pl->d.nch)
+            return fail(QC_ERR_ARG, "qc_set_poly_orders: order %d of row %zu outside [2, nch=%d]", orders[r], r, pl->d.nch);
+    if (s.orders.n != rows) QC_CUDA(s.orders.alloc(rows));
+    QC_CUDA(cudaMemcpyAsync(s.orders.p, orders, rows * sizeof(int), cudaMemcpyHostToDevice, pl->ctx->stream));
+    QC_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+    s.truncated = true;
     return QC_OK;
 }
 
@@ -829,6 +851,7 @@ static int32_t run_sweep(qc_plan *pl, const qc_sweep_args *a, bool single_step, 
         g.psi = pl->psi.p; g.v = ap.v ? ap.v : pl->v.p; g.v_stride = (!ap.v && pl->v_batched) ? 2LL * d.np : 0;
         g.kin = ap.kin ? ap.kin : pl->kin.p;
         g.tw1 = pl->tw1.p; g.tw2 = pl->tw2.p; g.xp = ps.xp.p; g.dv = ps.dv.p; g.sc = ps.sc.p;
+        g.orders = (ps.truncated && !ap.active && !local) ? ps.orders.p : nullptr;
         g.poly_stride = ps.batched; g.dx = pl->dx.p; g.dx_stride = pl->dx_batched;
         g.E_base = pl->E_base.p; g.E_stride = 1; g.expL = pl->expL[a->poly_slot].p; g.expL_stride = pl->expL_batched[a->poly_slot];
         g.ctl = pl->ctl.p; g.ctl_stride = pl->ctl_batched; g.E_step = pl->E_step.p; g.E_out = pl->E_out.p;
@@ -866,9 +889,13 @@ static int32_t run_sweep(qc_plan *pl, const qc_sweep_args *a, bool single_step, 
         bool packed = pl->log2n <= 9 && g.run_count > 2 * pl->ctx->sm_count;
         if (const char *e = getenv("QC_GRID_PACK")) packed = pl->log2n <= 9 && atoi(e) != 0;
         if (packed) {
+            bool four = QC_GRID_VAR_DEFAULT == 1;       // np = 512: four runs per CTA with the tensor-memory hand-over
+            if (const char *e = getenv("QC_GRID_TMP")) four = atoi(e) != 0;
             switch (pl->log2n) {
                 case 8: return launch_grid<8, false, false, 4, true>(pl, g, lst);
-                case 9: return launch_grid<9, false, false, 2, false>(pl, g, lst);
+                case 9:
+                    if (four) return launch_grid<9, false, false, 4, false, 1>(pl, g, lst);
+                    return launch_grid<9, false, false, 2, false>(pl, g, lst);
             }
         }
         // kernel variants of the plain form (qc_grid.cuh, GridCfg::VAR); QC_GRID_VAR overrides the default (A/B runs)
@@ -898,7 +925,9 @@ static int32_t run_sweep(qc_plan *pl, const qc_sweep_args *a, bool single_step, 
     n.renorm = a->renorm; n.field_mode = mode; n.reversed_E = a->reversed_E; n.write_E_base = a->write_E_base;
     n.l_first = a->l_first; n.nsteps = a->nsteps; n.single_step = single_step ? 1 : 0; n.nthreads = pl->nthreads;
     n.psi = pl->psi.p; n.vdiag = pl->v.p; n.v_stride = pl->v_batched; n.uwd = pl->uwd.p; n.uwd_stride = pl->uwd_batched;
-    n.xp = ps.xp.p; n.dv = ps.dv.p; n.sc = ps.sc.p; n.poly_stride = ps.batched; n.dx = pl->dx.p; n.dx_stride = pl->dx_batched;
+    n.xp = ps.xp.p; n.dv = ps.dv.p; n.sc = ps.sc.p; n.poly_stride = ps.batched;
+    n.orders = (ps.truncated && !ap.active) ? ps.orders.p : nullptr;
+    if (const char *e = getenv("QC_NLEVEL_RETIRE")) n.no_retire = atoi(e) == 0; n.dx = pl->dx.p; n.dx_stride = pl->dx_batched;
     n.E_base = pl->E_base.p; n.E_stride = 1; n.s_env = pl->s_env.p; n.s_stride = pl->s_batched;
     n.ctl = pl->ctl.p; n.ctl_stride = pl->ctl_batched; n.a0 = pl->a0.p; n.E_step = pl->E_step.p; n.E_out = pl->E_out.p;
     n.traj_in = a->traj_read >= 0 ? pl->traj[a->traj_read].p : nullptr;

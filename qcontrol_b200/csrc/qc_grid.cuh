@@ -61,6 +61,7 @@ struct GridParams {
     const double *xp;            // [nch]
     const cd *dv;                // [pb][nch]
     const double *sc;            // [pb][4] emin emax t_sc eL
+    const int *orders;           // [pb] polynomial terms summed per run (truncated series, opt-in), or null = nch
     int poly_stride;             // 0 or 1 (in runs)
     const double *dx;            // [db]
     int dx_stride;
@@ -123,9 +124,16 @@ struct GridCfg {
     // 16 doubles of reduction scratch; then 32 doubles per CTA
     static constexpr int LEVEL_ELEMS = (ILV || TMH) ? BUF : BUF + 2 * N;     // complex elements of shared memory per level
     static constexpr size_t RUN_BYTES = sizeof(cd) * (size_t)(2 * LEVEL_ELEMS + MAXCH) + sizeof(double) * (size_t)(MAXCH + 16);
+    // TMA staging of the trajectory stream (plain TMH form): the slice of the previous opposite sweep that the field
+    // law of the NEXT time step reads is fetched by one cp.async.bulk (the TMA engine's 1-D bulk copy, SASS UBLKCP)
+    // into a shared-memory buffer while the current step computes; an mbarrier with a byte count says when it landed.
+    // The shared memory for it is what the tensor-memory hand-over freed.
+    static constexpr bool TMA_SLICE = TMH && !PK;
+    static constexpr size_t PLAIN_BYTES =
+        sizeof(cd) * (size_t)(NLEV_CTA * LEVEL_ELEMS) + sizeof(double) * (size_t)(3 * MAXCH + 32 + LC_STRIDE + LS_COUNT);
+    static constexpr size_t SLICE_OFFSET = (PLAIN_BYTES + 127) / 128 * 128;
     static constexpr size_t SMEM_BYTES =
-        PK ? RPC * RUN_BYTES + sizeof(double) * 32
-           : sizeof(cd) * (size_t)(NLEV_CTA * LEVEL_ELEMS) + sizeof(double) * (size_t)(3 * MAXCH + 32 + LC_STRIDE + LS_COUNT);
+        PK ? RPC * RUN_BYTES + sizeof(double) * 32 : TMA_SLICE ? SLICE_OFFSET + sizeof(cd) * (size_t)N + 16 : PLAIN_BYTES;
 };
 
 // skewed position of element (k2, n3) inside a lane group's private 16*R3 region
@@ -139,6 +147,31 @@ __device__ __forceinline__ void bar_sync(int id, int nthreads) {
 }
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---- TMA 1-D bulk copy global -> shared memory, completion counted in bytes on an mbarrier -------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(b), "r"(parity)
+            : "memory");
+    } while (!done);
 }
 
 // ---- tensor memory as a per-thread scratchpad -----------------------------------------------------------
@@ -349,9 +382,14 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
     // Packed form: interleaved layout one id per run (1 + rslot); level-per-warp layout five per run (four "available"
     // ids and one for sums).  A "phi has been read" handshake is not needed: the buffers alternate with the order
     // parity, and a level passes its wait for the partner's order j+1 only after the partner has finished order j.
-    // TMP: seven per run (two level barriers, four "available" ids, one for sums).
-    const int bar_run = TMP ? 1 + 7 * rslot + 6 : PKL ? 1 + 5 * rslot + 4 : 1 + rslot;
+    // TMP: seven per run (two level barriers, four "available" ids, one for sums).  RDV (TMP with a level per warp,
+    // np = 512, four runs per CTA): a run is two warps, and 4 x 5 ids would not fit the 15 a CTA has, so the hand-over
+    // is a symmetric rendezvous of the two warps once per order (id 1 + RPC + rslot) -- the double-buffered phi in
+    // tensor memory still lets either warp run ahead into the transform of the next order
+    constexpr bool RDV = TMP && WPL == 1;
+    const int bar_run = RDV ? 1 + rslot : TMP ? 1 + 7 * rslot + 6 : PKL ? 1 + 5 * rslot + 4 : 1 + rslot;
     const int bar_full = TMP ? 1 + 7 * rslot + 2 : PKL ? 1 + 5 * rslot : 3;
+    const int bar_rdv = 1 + RPC + rslot;
     auto both_sums = [&](double val, double &s0, double &s1) {
         if (CL) cluster_sums<C::NTHREADS>(val, s_red, tid, lev, s0, s1);
         else if (PKL) packed_level_sums<RW>(val, s_red, rtid, bar_run, s0, s1);
@@ -436,6 +474,11 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     const cd *traj_in = p.traj_in ? p.traj_in + (long long)run * (p.nt_max + 1) * N : nullptr;
+    // TMA staging of the stored trajectory (C::TMA_SLICE): one slice ahead of the time loop
+    cd *s_slice = reinterpret_cast<cd *>(smem_raw + (C::TMA_SLICE ? C::SLICE_OFFSET : 0));
+    uint64_t *s_mbar = reinterpret_cast<uint64_t *>(s_slice + N);
+    const bool staged = C::TMA_SLICE && traj_in && !p.single_step && (p.field_mode == 1 || p.field_mode == 2);
+    uint32_t slice_phase = 0;
     cd *traj_out = p.traj_out ? p.traj_out + (long long)run * (p.nt_max + 1) * N : nullptr;
     const long long erun = (long long)p.E_stride * run * (p.nt_max + 1);
     const long long xrun = (long long)p.expL_stride * run * (p.nt_max + 1);
@@ -443,7 +486,12 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
     // which level records / reads trajectories: forward sweeps record level 0 and read the stored
     // level 1 of chi; backward sweeps record level 1 and read level 0 of psi (fitter.py:700-706, 791-796)
     const int ov_lev = p.field_mode == 2 ? 1 : 0;
-    const int last_j = p.nch - 2;
+    const int last_j = (p.orders ? p.orders[prun] : p.nch) - 2;
+    if (staged) {
+        if (tid == 0) mbar_init(s_mbar, 1);
+        __syncthreads();
+        if (tid == 0 && p.l_first <= nt) tma_load_1d(s_slice, traj_in + (long long)(nt - p.l_first) * N, (uint32_t)(N * sizeof(cd)), s_mbar);
+    }
 
     for (int l = p.l_first; l < p.l_first + p.nsteps && l <= nt && (!PK || valid); ++l) {
         const bool start_only = (l == 0);   // start(): only the initial field is evaluated (propagation.py:360-361)
@@ -487,7 +535,8 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
         } else {
             double part = 0.0;
             if (lev == ov_lev) {
-                const cd *tr = traj_in + (long long)(nt - l) * N;
+                const cd *tr = staged ? s_slice : traj_in + (long long)(nt - l) * N;
+                if (staged) mbar_wait(s_mbar, slice_phase);      // the bulk copy of this step's slice has landed
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const cd c = tr[t + TPL * i];
@@ -499,6 +548,14 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
             both_sums(part, t0s, t1s);
             const double tot = t0s + t1s;
             E = -2.0 * (tot * dx) / h_lambda;
+            if (staged) {
+                // every thread is past the CTA-wide barriers of the sums, so the buffer has been read: fetch the slice
+                // of the next step behind the 63 polynomial orders of this one
+                slice_phase ^= 1u;
+                const int ln = l + 1;
+                if (tid == 0 && ln <= nt && ln < p.l_first + p.nsteps)
+                    tma_load_1d(s_slice, traj_in + (long long)(nt - ln) * N, (uint32_t)(N * sizeof(cd)), s_mbar);
+            }
         }
         if (writer && !p.single_step) {
             E_out[l] = cmk(E, LOCAL ? s_lc[LC_FM] : 0.0);      // local control: the multiplier rides in the imaginary slot
@@ -542,7 +599,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
                 TmemTwiddles tw(t_tw1);
                 dft16_table_out<false>(a, tw, [&](int k1, cd val) { bufA[k1 * S1 + t] = val; });
             }
-            if (TMH) {
+            if (TMH && !RDV) {
                 // hand-over through tensor memory: the asynchronous stores of phi have long landed behind the
                 // butterflies of pass 1; make them visible to the partner warp and signal "phi of this parity is there"
                 tmem_wait_st();
@@ -614,7 +671,12 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
             }
             // pointwise part (hamil_2d.py:60-71, phys_base.py:98-111) and accumulation (phys_base.py:170-172),
             // in chunks of four grid points: psi and own phi from TMEM, the other level's phi from shared memory
-            if (NAMED) bar_sync(BAR_FULL_OTH + par, HN);
+            if (NAMED && !RDV) bar_sync(BAR_FULL_OTH + par, HN);
+            if (RDV) {
+                tmem_wait_st();
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                bar_sync(bar_rdv, HN);
+            }
             if (TMH) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (CL) cl_wait();
             tmem_wait_st();

@@ -17,6 +17,7 @@ struct NLevelParams {
     int batch, nb, nbp, nch, nt_max, hamil;
     int renorm, field_mode, reversed_E, write_E_base;
     int l_first, nsteps, single_step;
+    int no_retire;               // diagnostics (QC_NLEVEL_RETIRE=0): every warp runs the whole launch like in round 1
     long long nthreads;          // batch * nbp
     cd *psi;                     // [batch][nb][NL]
     const double *vdiag;         // [vb][NL]  the constant arrays v[n][1] (two_levels only)
@@ -26,6 +27,7 @@ struct NLevelParams {
     const double *xp;            // [nch]
     const cd *dv;                // [pb][nch]
     const double *sc;            // [pb][4]
+    const int *orders;           // [pb] polynomial terms summed per run (opt-in truncation) or null
     int poly_stride;
     const double *dx;
     int dx_stride;
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(128) nlevel_sweep_kernel(NLevelParams p) {
     int warp_last = (in_range && !retired) ? nt : -1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
-    const int l_end = p.single_step ? p.l_first + p.nsteps : min(p.l_first + p.nsteps, warp_last + 1);
+    const int l_end = (p.single_step || p.no_retire) ? p.l_first + p.nsteps : min(p.l_first + p.nsteps, warp_last + 1);
     const double U = p.uwd ? p.uwd[(long long)p.uwd_stride * run * 3 + 0] : 0.0;
     const double W = p.uwd ? p.uwd[(long long)p.uwd_stride * run * 3 + 1] : 0.0;
     const double delta = p.uwd ? p.uwd[(long long)p.uwd_stride * run * 3 + 2] : 0.0;
@@ -92,6 +94,7 @@ __global__ void __launch_bounds__(128) nlevel_sweep_kernel(NLevelParams p) {
     sincos(-2.0 * t_sc * (emax + emin) / (emax - emin), &ph_s, &ph_c);
     const cd phase = cmk(ph_c, ph_s);
     const cd *dv = p.dv + prun * p.nch;
+    const int nterms = p.orders ? p.orders[prun] : p.nch;
     constexpr int NCR = NCH > 0 ? NCH : 1;
     double xp_r[NCR];
     cd dv_r[NCR];
@@ -243,9 +246,9 @@ __global__ void __launch_bounds__(128) nlevel_sweep_kernel(NLevelParams p) {
         if (NCH > 0) {
 #pragma unroll
             for (int j = 0; j < NCR - 1; ++j)
-                if (j < p.nch - 1) order(xp_r[j], dv_r[j + 1]);
+                if (j < nterms - 1) order(xp_r[j], dv_r[j + 1]);
         } else {
-            for (int j = 0; j < p.nch - 1; ++j) order(p.xp[j], dv[j + 1]);
+            for (int j = 0; j < nterms - 1; ++j) order(p.xp[j], dv[j + 1]);
         }
         double nsum = 0.0;
         double nl[NL];

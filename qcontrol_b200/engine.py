@@ -150,6 +150,18 @@ class Plan:
         sc = np.empty((rows, 4), np.float64)
         sc[:, 0], sc[:, 1], sc[:, 2], sc[:, 3] = emin, emax, t_sc, eL
         check(lib.qc_set_poly(self._h, int(slot), _ptr(xp), _ptr(dv.view(np.float64)), _ptr(sc), int(batched)))
+        self._poly_batched = getattr(self, "_poly_batched", {})
+        self._poly_batched[int(slot)] = bool(batched)
+
+    def set_poly_orders(self, slot, orders=None):
+        """Opt-in truncation of the interpolation series of ``slot`` to orders[run] terms (None: the full series)."""
+        if orders is None:
+            check(lib.qc_set_poly_orders(self._h, int(slot), None, 0))
+            return
+        batched = getattr(self, "_poly_batched", {}).get(int(slot), False)      # same row layout as set_poly's dv
+        o = np.ascontiguousarray(np.atleast_1d(orders), dtype=np.int32)
+        assert o.shape[0] == (self.batch if batched else 1), (o.shape, batched, self.batch)
+        check(lib.qc_set_poly_orders(self._h, int(slot), o.ctypes.data_as(C.POINTER(C.c_int32)), int(batched)))
 
     def set_state(self, psi):
         psi = _c128(psi, self.state_shape)

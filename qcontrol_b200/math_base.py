@@ -130,3 +130,38 @@ def newton_tables_batched(nch, t_sc):
         prod *= (xp[i] - xp[i - 1])
         dv[:, i] = (f[:, i] - dv[:, 0] - tail) / prod
     return xp, dv
+
+
+_PARTIAL_BOUND_CACHE = {}
+
+
+def partial_product_bounds(nch):
+    """B_j = max over z in [-2, 2] of |prod_{m<j} (z - xp_m)| for the nodes in the reference's visiting order: the
+    norm of the j-th Newton basis operator prod_{m<j}(Hn - xp_m) for a Hermitian Hn with spectrum in [-2, 2]."""
+    hit = _PARTIAL_BOUND_CACHE.get(nch)
+    if hit is None:
+        xp = numpy.array([2.0 * math.cos(numpy.float64(2 * j + 1) / numpy.float64(2 * nch) * math.pi)
+                          for j in _fold_order(nch)])
+        z = numpy.concatenate([numpy.linspace(-2.0, 2.0, 16001), xp])
+        prod = numpy.ones_like(z)
+        hit = numpy.empty(nch)
+        for j in range(nch):
+            hit[j] = numpy.abs(prod).max()
+            prod = prod * (z - xp[j])
+        hit *= 1.001                      # sampling margin
+        _PARTIAL_BOUND_CACHE[nch] = hit
+    return hit
+
+
+def truncation_order(nch, dv, tol):
+    """Smallest J >= 2 such that dropping the terms j >= J of the interpolation series changes P(Hn) psi by at most
+    ``tol`` * |psi|:  sum_{j>=J} |dv_j| * B_j <= tol  (OPT-IN, see qc_set_poly_orders).  The reference sums all nch
+    terms; behind the converged part its divided differences are round-off of size 1e-17, so for small
+    scaled times most of the orders carry nothing: t_sc = 0.2 (single_harm) -> 10 of 64 at tol = 1e-11, t_sc = 3.7
+    (the shipped Krotov input) -> 30 of 64; t_sc >= 14 needs them all."""
+    dv = numpy.asarray(dv)
+    B = partial_product_bounds(nch)
+    tail = numpy.cumsum((numpy.abs(dv) * B)[..., ::-1], axis=-1)[..., ::-1]
+    ok = tail <= tol
+    J = numpy.where(ok.any(axis=-1), ok.argmax(axis=-1), nch)
+    return numpy.maximum(J, 2).astype(numpy.int32)

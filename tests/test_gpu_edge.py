@@ -307,3 +307,55 @@ def test_memory_sized_sub_batches(ctx):
     pl.close()
     assert used <= est + (64 << 20), (used, est)          # the allocator rounds to 2 MiB pages
     assert used >= 0.5 * est
+
+
+def test_truncated_series_is_opt_in_and_within_its_bound(ctx, golden, monkeypatch):
+    """OPT-IN truncation of the interpolation series (qc_set_poly_orders, control.GridBatch(poly_tol=...)): off by
+    default -- the plain path sums all nch terms like the reference --; with a per-step bound of 1e-11 the orders drop
+    to 10 of 64 (single_harm, t_sc = 0.2) and 30 of 64 (Krotov, t_sc = 3.7), and the result stays within north_star's
+    1e-10 of the REFERENCE's own output: one step on the reference fixtures, a whole prescribed sweep, a whole Krotov
+    optimisation (tables to 1e-7: the field law divides overlaps by h_lambda = 0.0066)."""
+    from qcontrol_b200 import control, engine, math_base
+    from tests.test_gpu_parity import _problem, l2
+    monkeypatch.delenv("QC_POLY_TOL", raising=False)
+    for name, lo, hi in (("harm", 8, 12), ("krotov", 25, 45), ("morse", 64, 64)):
+        g = golden("one_step_" + name)
+        n = g["v"].shape[1]
+        pl = engine.Plan(ctx, engine.HAMIL_NONTRIV, n, 2, 1, int(g["nch"]), 2, 4)
+        pl.set_static(g["v"], np.ascontiguousarray(g["akx2"].real), None, float(g["dx"]))
+        t_sc = float(g["t_sc"])
+        xp, dv = math_base.newton_table(int(g["nch"]), t_sc)
+        J = int(math_base.truncation_order(int(g["nch"]), dv, 1e-11))
+        assert lo <= J <= hi, (name, J)
+        pl.set_poly(0, xp, dv, float(g["emin"]), float(g["emax"]), t_sc, float(g["eL"]))
+        outs = []
+        for orders in (None, [J]):
+            pl.set_poly_orders(0, orders)      # set_poly got an unbatched table: one order for the whole plan
+            pl.set_state(np.broadcast_to(g["psi_in"], (2, 1) + g["psi_in"].shape))
+            pl.prop_step(0, float(g["E_f"]))
+            outs.append(pl.get_state()[0, 0])
+            assert l2(outs[-1], g["psi_out_f"], float(g["dx"])) <= 1e-10, (name, orders)
+        if J < int(g["nch"]):
+            assert 0.0 < l2(outs[0], outs[1], float(g["dx"])) <= 1e-11       # it did change, within the bound
+        with pytest.raises(Exception):
+            pl.set_poly_orders(0, [1])
+        pl.close()
+    # whole runs
+    g = golden("fit_single_harm")
+    pb = _problem(g)
+    gb = control.GridBatch([pb], ctx=ctx, poly_tol=1e-11)
+    assert 8 <= int(gb.poly_orders[control.FORWARD][0]) <= 12
+    out = gb.propagate()
+    k = int(np.argmax(g["iter_0f__basis_0__l"]))
+    assert int(g["iter_0f__basis_0__l"][k]) == pb.nt
+    assert l2(out[0, 0], g["iter_0f__basis_0__psi"][k], pb.dx) <= 1e-10 * pb.nt
+    gb.close()
+    g = golden("fit_krotov_256")
+    pb = _problem(g)
+    monkeypatch.setenv("QC_POLY_TOL", "1e-11")                   # the whole-application switch
+    gb = control.GridBatch([pb, pb], ctx=ctx)
+    assert gb.poly_tol == 1e-11 and int(gb.poly_orders[control.FORWARD][0]) < 64
+    hist = gb.run_krotov()
+    tab = _rows(hist[0])
+    assert tab.shape == g["iter_tab"].shape and np.allclose(tab, g["iter_tab"], rtol=1e-7, atol=0), tab - g["iter_tab"]
+    gb.close()

@@ -50,7 +50,7 @@ def main():
             tm = task_manager.create(c)
         pbs.append(newcheb.problem_from(c, tm))
     for copies in a.copies:
-        runs = pbs * copies
+        runs = sorted(pbs * copies, key=lambda p: -p.nt)      # runs of similar length share warps (they retire together)
         nb = control.NLevelBatch(runs, ctx=ctx)
         # one call; iteration 0 carries one-time work (field tables of the backward sweep, first-touch of the host
         # arrays), so the rate is taken over iterations 1 ... iters-1 from the loop's own time marks

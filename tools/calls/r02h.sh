@@ -1,0 +1,10 @@
+#!/bin/bash
+# round 2, call h: np = 512 four-runs-per-CTA form; full suite; size sweep
+set -x
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_edge.py -x -q -m gpu -k "tensor_memory or ragged_krotov or packed_form or one_step_vs_oracle" > gpurun_out/r02h_pytest_512.log 2>&1
+echo "rc=$?" >> gpurun_out/r02h_pytest_512.log
+timeout 300 python tools/size_sweep.py > gpurun_out/r02h_size_sweep.log 2>&1
+timeout 300 python tools/form_compare.py QC_GRID_TMP 512 0 > gpurun_out/r02h_form512.log 2>&1
+timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/r02h_pytest_full.log 2>&1
+echo done
