@@ -12,6 +12,7 @@
 
 #include "../../include/qcontrol_b200.h"
 #include "qc_grid.cuh"
+#include "qc_grid8.cuh"
 #include "qc_grid2d.cuh"
 #include "qc_nlevel.cuh"
 
@@ -103,7 +104,7 @@ struct qc_plan {
     long long nthreads;      // batch * nbp
     size_t state_elems;      // batch*nb*nlevs*np
     size_t traj_elems;
-    DevBuf<cd> psi, E_base, expL[2], s_env, E_out, a0, E_step, tw1, tw2, goal, gc, tmp_row;
+    DevBuf<cd> psi, E_base, expL[2], s_env, E_out, a0, E_step, tw1, tw2, tw8, goal, gc, tmp_row;
     DevBuf<cd> traj[2];
     DevBuf<cd> snap[4];
     DevBuf<double> v, kin, uwd, dx, ctl, norms;
@@ -373,6 +374,22 @@ static void fill_twiddles(int log2n, std::vector<cd> &t1, std::vector<cd> &t2) {
         }
 }
 
+// tables of the 512-thread form at np = 2048 (qc_grid8.cuh): forward values exp(-2 pi i m / M)
+static void fill_twiddles8(std::vector<cd> &t) {
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    auto root = [&](int m, int M) {
+        const long double ang = -two_pi * (long double)(m % M) / (long double)M;
+        return qc::cmk((double)cosl(ang), (double)sinl(ang));
+    };
+    t.clear();
+    for (int k1 = 0; k1 < 8; ++k1)
+        for (int T = 0; T < 256; ++T) t.push_back(root(k1 * T, 2048));
+    for (int k2 = 0; k2 < 8; ++k2)
+        for (int m = 0; m < 32; ++m) t.push_back(root(k2 * m, 256));
+    for (int k3 = 0; k3 < 8; ++k3)
+        for (int n = 0; n < 4; ++n) t.push_back(root(k3 * n, 32));
+}
+
 template <typename T>
 static int32_t upload(qc_plan *pl, DevBuf<T> &buf, const void *host, size_t count) {
     if (buf.n != count) QC_CUDA(buf.alloc(count));
@@ -575,6 +592,11 @@ extern "C" int32_t qc_plan_create(qc_context *ctx, const qc_plan_desc *desc, qc_
         fill_twiddles(pl->log2n, t1, t2);
         int32_t rc = upload(pl, pl->tw1, t1.data(), t1.size());
         if (rc == QC_OK) rc = upload(pl, pl->tw2, t2.data(), t2.size());
+        if (rc == QC_OK && pl->log2n == 11) {
+            std::vector<cd> t8;
+            fill_twiddles8(t8);
+            rc = upload(pl, pl->tw8, t8.data(), t8.size());
+        }
         if (rc != QC_OK) {
             qc_plan_destroy(pl);
             return rc;
@@ -620,7 +642,7 @@ extern "C" int32_t qc_plan_destroy(qc_plan *pl) {
     cudaSetDevice(pl->ctx->device);
     cudaStreamSynchronize(pl->ctx->stream);
     pl->psi.release(); pl->E_base.release(); pl->expL[0].release(); pl->expL[1].release(); pl->s_env.release(); pl->E_out.release();
-    pl->a0.release(); pl->E_step.release(); pl->tw1.release(); pl->tw2.release(); pl->goal.release();
+    pl->a0.release(); pl->E_step.release(); pl->tw1.release(); pl->tw2.release(); pl->tw8.release(); pl->goal.release();
     pl->gc.release(); pl->tmp_row.release(); for (auto &b : pl->snap) b.release(); pl->traj[0].release(); pl->traj[1].release();
     pl->v.release(); pl->kin.release(); pl->uwd.release(); pl->dx.release(); pl->ctl.release(); pl->norms.release();
     for (auto &s : pl->poly) { s.xp.release(); s.sc.release(); s.dv.release(); s.orders.release(); }
@@ -789,6 +811,20 @@ static int32_t launch_grid(qc_plan *pl, const qc::GridParams &gp, cudaStream_t s
     return QC_OK;
 }
 
+static int32_t launch_grid8(qc_plan *pl, const qc::GridParams &gp, cudaStream_t stream) {
+    typedef qc::Grid8Cfg C;
+    static bool attr_done[64] = {false};
+    const int dev = pl->ctx->device;
+    if (!attr_done[dev & 63]) {
+        QC_CUDA(cudaFuncSetAttribute(qc::grid8_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+        attr_done[dev & 63] = true;
+    }
+    qc::grid8_sweep_kernel<<<gp.run_count, C::NTHREADS, C::SMEM_BYTES, stream>>>(gp);
+    pl->ctx->launches++;
+    QC_CUDA(cudaGetLastError());
+    return QC_OK;
+}
+
 template <int NL>
 static int32_t launch_nlevel(qc_plan *pl, const qc::NLevelParams &np_) {
     const int threads = 128;
@@ -850,7 +886,7 @@ static int32_t run_sweep(qc_plan *pl, const qc_sweep_args *a, bool single_step, 
         g.l_first = a->l_first; g.nsteps = a->nsteps; g.single_step = single_step ? 1 : 0;
         g.psi = pl->psi.p; g.v = ap.v ? ap.v : pl->v.p; g.v_stride = (!ap.v && pl->v_batched) ? 2LL * d.np : 0;
         g.kin = ap.kin ? ap.kin : pl->kin.p;
-        g.tw1 = pl->tw1.p; g.tw2 = pl->tw2.p; g.xp = ps.xp.p; g.dv = ps.dv.p; g.sc = ps.sc.p;
+        g.tw1 = pl->tw1.p; g.tw2 = pl->tw2.p; g.tw8 = pl->tw8.p; g.xp = ps.xp.p; g.dv = ps.dv.p; g.sc = ps.sc.p;
         g.orders = (ps.truncated && !ap.active && !local) ? ps.orders.p : nullptr;
         g.poly_stride = ps.batched; g.dx = pl->dx.p; g.dx_stride = pl->dx_batched;
         g.E_base = pl->E_base.p; g.E_stride = 1; g.expL = pl->expL[a->poly_slot].p; g.expL_stride = pl->expL_batched[a->poly_slot];
@@ -914,7 +950,10 @@ static int32_t run_sweep(qc_plan *pl, const qc_sweep_args *a, bool single_step, 
                 }
                 return launch_grid<10>(pl, g, lst);
             case 11:
-                if (var == 1) return launch_grid<11, false, false, 0, false, 1>(pl, g, lst);
+                // 512-thread form (qc_grid8.cuh): sweeps of the prescribed / Krotov field laws
+                if (var == 2 && !single_step && !ap.cplx && !ap.active && mode <= QC_FIELD_KROTOV_BWD)
+                    return launch_grid8(pl, g, lst);
+                if (var >= 1) return launch_grid<11, false, false, 0, false, 1>(pl, g, lst);
                 return launch_grid<11>(pl, g, lst);
         }
         return fail(QC_ERR_ARG, "qc_sweep: unsupported np");

@@ -81,6 +81,7 @@ struct GridParams {
     const double *lc_t;          // [batch][nt_max+1] step times t_l
     const double *lc_rt;         // [nch][nch] transposed partial products of the Newton table
     const double *lc_rdiag;      // [nch] reciprocal pivots
+    const cd *tw8;               // np = 2048, 512-thread form (qc_grid8.cuh): [8][256] w_2048^(k1 T), [8][32] w_256^(k2 m), [8][4] w_32^(k3 n)
 };
 
 // CL = false: one CTA holds both levels of a run.  CL = true: a cluster of two CTAs, one level each, on two SMs --
