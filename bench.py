@@ -465,7 +465,10 @@ def e2e_api_block(rank, world, local_dev, runs, nt):
             "krotov_iterations": iters, "sweeps_per_run": sweeps,
             "call": "batch.expand_substitutions + newcheb.run_variants + batch.gather_results (strong scaling over the ranks)",
             "rank0_split_s": {k: (round(v, 4) if isinstance(v, float) else v) for k, v in tm.items()},
-            "setup_s": tm.get("config_s", 0.0) + tm.get("task_setup_s", 0.0) + tm.get("plan_setup_s", 0.0)}
+            "setup_s": tm.get("config_s", 0.0) + tm.get("task_setup_s", 0.0) + tm.get("plan_setup_s", 0.0),
+            "setup_exposed_s": tm.get("config_s", 0.0) + tm.get("setup_wait_s", 0.0),
+            "pipeline": "the batch is cut into pieces of two waves of CTAs; task and plan set-up of piece k + 1 run on a second "
+                        "thread and stream beside the control loops of piece k (setup_exposed_s = what the GPU waited for)"}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -98,6 +98,16 @@ int32_t qc_measure_fp64_peak(qc_context *ctx, double *tflops);
  * (psi_tlist / chi_tlist, fitter.py:322-329); here they live in HBM, so batch entry points size their plans with
  * this and qc_plan_footprint instead of failing with QC_ERR_NOMEM */
 int32_t qc_mem_info(qc_context *ctx, int64_t *free_bytes, int64_t *total_bytes);
+/* number of SMs of the context's GPU: batch entry points cut big batches into pieces of whole waves of CTAs so that the
+ * host set-up of one piece overlaps the propagation of the previous one (the reference farms its jobs over a thread
+ * pool instead, newcheb.py:656-659) */
+int32_t qc_sm_count(qc_context *ctx, int32_t *sm_count);
+/* Reserve `bytes` of device memory as an arena from which the plans of this device are cut until it is given back
+ * with bytes = 0 (or the last context of the device is destroyed).  A batch entry point that sets the next sub-batch up
+ * beside the propagation of the current one reserves its working set while the GPU is idle: an allocation by the
+ * driver beside a running sweep returns only when the sweep ends.  Requests the arena cannot serve fall back to the
+ * driver. */
+int32_t qc_pool_reserve(qc_context *ctx, int64_t bytes);
 
 /* ---- plan ---------------------------------------------------------------- */
 int32_t qc_plan_create(qc_context *ctx, const qc_plan_desc *desc, qc_plan **out);

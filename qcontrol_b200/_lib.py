@@ -16,7 +16,7 @@ ABI_VERSION = 1
 # every symbol include/qcontrol_b200.h declares
 SYMBOLS = (
     "qc_abi_version", "qc_last_error", "qc_create", "qc_destroy", "qc_synchronize", "qc_timer_start",
-    "qc_timer_stop", "qc_launch_count", "qc_measure_fp64_peak", "qc_mem_info", "qc_plan_create", "qc_plan_destroy",
+    "qc_timer_stop", "qc_launch_count", "qc_measure_fp64_peak", "qc_mem_info", "qc_sm_count", "qc_pool_reserve", "qc_plan_create", "qc_plan_destroy",
     "qc_plan_footprint",
     "qc_set_static", "qc_set_poly", "qc_set_poly_orders", "qc_set_state", "qc_get_state", "qc_set_step_scalars", "qc_set_control",
     "qc_sweep", "qc_prop_step", "qc_apply_hamil", "qc_set_instr_grid", "qc_instrument", "qc_set_local_control", "qc_get_local_state", "qc_set_local_state", "qc_get_fields", "qc_field_integral", "qc_get_norms", "qc_snapshot_set", "qc_snapshot_load", "qc_goal_overlap", "qc_krotov_terminal",
@@ -63,6 +63,8 @@ def _load():
         "qc_launch_count": (C.c_int64, [vp]),
         "qc_measure_fp64_peak": (i32, [vp, dp]),
         "qc_mem_info": (i32, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+        "qc_sm_count": (i32, [vp, C.POINTER(C.c_int32)]),
+        "qc_pool_reserve": (i32, [vp, C.c_int64]),
         "qc_plan_footprint": (i32, [C.POINTER(PlanDesc), C.POINTER(C.c_int64)]),
         "qc_plan_create": (i32, [vp, C.POINTER(PlanDesc), C.POINTER(vp)]),
         "qc_plan_destroy": (i32, [vp]),

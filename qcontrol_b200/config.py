@@ -9,10 +9,26 @@ keep their defaults, as in the reference (config.py:27-64).
 """
 from __future__ import annotations
 
+import contextlib
 import copy
+import threading
 from enum import Enum
 
 import numpy
+
+_QUIET = threading.local()
+
+
+@contextlib.contextmanager
+def quiet():
+    """Silences the "parameter hasn't been provided" notes of load() for the calling THREAD (contextlib.redirect_stdout
+    swaps sys.stdout for every thread; batch set-up runs beside the control loops of the previous sub-batch)."""
+    prev = getattr(_QUIET, "on", False)
+    _QUIET.on = True
+    try:
+        yield
+    finally:
+        _QUIET.on = prev
 
 
 class _NamedEnum(Enum):
@@ -48,8 +64,9 @@ class ConfigurationBase:
             elif key in user_data:
                 raw = user_data[key]
             else:
-                print("Parameter '%s' hasn't been provided in the input json file. "
-                      "It will be calculated automatically or the default value will be used: %s" % (key, str(default)))
+                if not getattr(_QUIET, "on", False):
+                    print("Parameter '%s' hasn't been provided in the input json file. "
+                          "It will be calculated automatically or the default value will be used: %s" % (key, str(default)))
                 continue
             # bool is tested after int on purpose: the reference does the same (config.py:41-44), so a
             # JSON true/false stored under a bool default goes through int()

@@ -158,6 +158,9 @@ def field_integral(Et, t_step, exact=True):
 TRAJ_TASKS = ("optimal_control_krotov", "optimal_control_unit_transform")
 
 
+_EXPL_MEMO = {}      # (direction, carrier, nu, T, t_step, nt, pcos, w_list) -> exp_L[l] of GridBatch._upload_static
+
+
 class _BatchBase:
     def __init__(self, problems: Sequence, ctx: eng.Context = None, device: int = 0, store_traj=None, poly_tol=None):
         """store_traj: allocate the two trajectory buffers [batch][nt_max+1][np] (grid) -- None = only for the task
@@ -179,17 +182,25 @@ class _BatchBase:
                    (p0.np_, p0.nlevs, p0.nb, p0.nch, p0.hamil, p0.hf_hide), "a batch shares one plan shape"
         self.nt = np.array([p.nt for p in self.pbs])
         self.nt_max = int(self.nt.max())
+        _t = [time.perf_counter()]
         self.plan = eng.Plan(self.ctx, _HAMIL_CODE[p0.hamil], p0.np_, p0.nlevs, p0.nb, p0.nch, self.B, self.nt_max,
                              hf_hide=p0.hf_hide, store_traj=store_traj)
+        _t.append(time.perf_counter())
         self.psi0 = np.stack([p.psi0 for p in self.pbs])
         self.psif = np.stack([p.psif for p in self.pbs])
         self.dx = np.array([float(p.dx) for p in self.pbs])
         self.plan.snapshot_set(0, self.psi0)      # SNAP_INIT
         self.plan.snapshot_set(1, self.psif)      # SNAP_GOAL
+        _t.append(time.perf_counter())
         self._upload_static()
+        _t.append(time.perf_counter())
         self._poly_dir = {}
         for slot, d in ((0, FORWARD), (1, BACKWARD)):
             self._upload_poly(slot, d)
+        _t.append(time.perf_counter())
+        if os.environ.get("QC_PROFILE_SETUP"):
+            print("batch set-up: plan %.3f s, snapshots %.3f s, static + exp_L %.3f s, polynomials %.3f s (%d runs)"
+                  % (_t[1] - _t[0], _t[2] - _t[1], _t[3] - _t[2], _t[4] - _t[3], self.B), flush=True)
 
     def _upload_poly(self, slot, direction):
         emins, emaxs, tscs, eLs = [], [], [], []
@@ -262,22 +273,28 @@ class GridBatch(_BatchBase):
             # exp_L[l] = csqrt(hf(t_l)) with the reference's scalar expressions (branch cut of cmath.sqrt).
             # The table depends on the time grid and the carrier only, which most runs of a batch share (the
             # variants of a template differ in a scalar or two): one evaluation per distinct (grid, carrier)
+            # the sub-batches of a big template share them too: a small memo across batches (_EXPL_MEMO)
             for slot, d in ((0, FORWARD), (1, BACKWARD)):
-                rows, seen = [], {}
-                for p in self.pbs:
+                table = np.zeros((self.B, self.nt_max + 1), np.complex128)
+                for b, p in enumerate(self.pbs):
                     key = None
                     if getattr(p, "carrier", None) and getattr(p, "nu", None) is not None:
-                        key = (p.carrier, float(p.nu), float(p.T), float(p.t_step), int(p.nt), float(p.pcos),
-                               tuple(float(w) for w in p.w_list))
-                    if key is None or key not in seen:
-                        row = [np.complex128(cmath.sqrt(p.laser_field_hf(np.float64(1.0), t, p.pcos, p.w_list)))
-                               for t in step_times(p, d)]
+                        # the exp carrier reads neither pcos nor w_list, cos / sin read pcos, the sets both
+                        # (task_manager.py:68-159)
+                        sets = p.carrier in ("cos_set", "sin_set")
+                        key = (d, p.carrier, float(p.nu), float(p.T), float(p.t_step), int(p.nt),
+                               0.0 if p.carrier == "exp" else float(p.pcos),
+                               tuple(float(w) for w in p.w_list) if sets else ())
+                    row = _EXPL_MEMO.get(key) if key is not None else None
+                    if row is None:
+                        row = np.array([np.complex128(cmath.sqrt(p.laser_field_hf(np.float64(1.0), t, p.pcos, p.w_list)))
+                                        for t in step_times(p, d)], np.complex128)
                         if key is not None:
-                            seen[key] = row
-                    else:
-                        row = seen[key]
-                    rows.append(row)
-                self.plan.set_exp_L(self._pad(rows), slot)
+                            if len(_EXPL_MEMO) >= 64:
+                                _EXPL_MEMO.clear()
+                            _EXPL_MEMO[key] = row
+                    table[b, :len(row)] = row
+                self.plan.set_exp_L(table, slot)
         self.plan.set_control(np.array([float(p.h_lambda) for p in self.pbs]), self.nt.astype(np.float64))
 
     def _vectorised(self):

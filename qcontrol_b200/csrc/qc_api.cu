@@ -1,10 +1,14 @@
 // C ABI of qcontrol_b200 (see include/qcontrol_b200.h).  Host-side plumbing only:
 // device buffers, uploads, kernel launches.  The numerics live in qc_grid.cuh
 // (FFT grid, kernel A) and qc_nlevel.cuh (N-level systems, kernel B).
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <iterator>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -58,8 +62,10 @@ struct qc_context {
     bool released;       // qc_destroy was called while plans were alive: freed with the last plan
 };
 
+static void pool_context_gone(int dev);
 static void context_free(qc_context *ctx) {
     cudaSetDevice(ctx->device);
+    pool_context_gone(ctx->device);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
@@ -70,18 +76,177 @@ static void context_free(qc_context *ctx) {
     delete ctx;
 }
 
+// ---- device memory pool ------------------------------------------------------------------------------------------
+// cudaFree waits for the whole device and cudaMalloc of a multi-GB trajectory buffer costs tens of milliseconds per GB;
+// a batch entry point that sets the next sub-batch up on a second thread while the GPU propagates the current one
+// (newcheb.run_variants) would stall on both.  Released buffers are therefore kept per device and handed out again to
+// requests of exactly the same size (the sub-batches of a shape group are alike); everything cached is given back to
+// the driver when an allocation fails, when qc_mem_info is asked for the free memory, and when the last context of the
+// device is destroyed.  Reused memory is as uninitialised as fresh memory: no caller may expect zeros.
+// An ARENA on top of that (qc_pool_reserve): one block reserved while the device is idle, from which every later
+// request is cut (first fit, coalescing free list).  A fresh cudaMalloc beside a running sweep -- every SM held by one
+// CTA for the whole sweep -- was measured to return only when the sweep ends (0.3-0.9 s per plan set-up).
+struct Arena {
+    char *base = nullptr;
+    size_t size = 0, live = 0;
+    bool released = false;
+    std::map<size_t, size_t> holes;            // offset -> length
+    void *cut(size_t bytes) {
+        bytes = (bytes + 511) / 512 * 512;
+        for (auto it = holes.begin(); it != holes.end(); ++it) {
+            if (it->second < bytes) continue;
+            const size_t off = it->first, len = it->second;
+            holes.erase(it);
+            if (len > bytes) holes.emplace(off + bytes, len - bytes);
+            live += bytes;
+            return base + off;
+        }
+        return nullptr;
+    }
+    bool owns(const void *q) const { return base && (const char *)q >= base && (const char *)q < base + size; }
+    void put(void *q, size_t bytes) {
+        bytes = (bytes + 511) / 512 * 512;
+        size_t off = (size_t)((char *)q - base);
+        live -= bytes;
+        auto nxt = holes.lower_bound(off);
+        if (nxt != holes.begin()) {
+            auto prv = std::prev(nxt);
+            if (prv->first + prv->second == off) {
+                off = prv->first;
+                bytes += prv->second;
+                holes.erase(prv);
+            }
+        }
+        if (nxt != holes.end() && off + bytes == nxt->first) {
+            bytes += nxt->second;
+            holes.erase(nxt);
+        }
+        holes.emplace(off, bytes);
+    }
+};
+
+struct DevPool {
+    std::mutex mu;
+    std::multimap<size_t, void *> blocks[64];
+    Arena arena[64];
+    int contexts[64] = {0};
+    // smallest cached block of at least `bytes` and at most four times that (the last sub-batch of a group is
+    // shorter than the others and may reuse their blocks; a small request must not swallow a trajectory buffer)
+    void *take(int dev, size_t bytes, size_t *cap) {
+        std::lock_guard<std::mutex> g(mu);
+        Arena &a = arena[dev & 63];
+        if (a.base && !a.released) {
+            if (void *q = a.cut(bytes)) {
+                *cap = bytes;
+                return q;
+            }
+        }
+        auto &m = blocks[dev & 63];
+        auto it = m.lower_bound(bytes);
+        if (it == m.end() || it->first > 4 * bytes) return nullptr;
+        void *q = it->second;
+        *cap = it->first;
+        m.erase(it);
+        return q;
+    }
+    void give(int dev, void *q, size_t bytes) {
+        void *dead = nullptr;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            Arena &a = arena[dev & 63];
+            if (a.owns(q)) {
+                a.put(q, bytes);
+                if (a.released && a.live == 0) {       // the last block of a released arena came back
+                    dead = a.base;
+                    a = Arena();
+                }
+            } else {
+                blocks[dev & 63].emplace(bytes, q);
+            }
+        }
+        if (dead) cudaFree(dead);
+    }
+    cudaError_t reserve(int dev, size_t bytes) {
+        std::lock_guard<std::mutex> g(mu);
+        Arena &a = arena[dev & 63];
+        if (a.base) return cudaSuccess;                // one arena per device at a time
+        void *q = nullptr;
+        cudaError_t e = cudaMalloc(&q, bytes);
+        if (e != cudaSuccess) return e;
+        a = Arena();
+        a.base = (char *)q;
+        a.size = bytes;
+        a.holes.emplace(0, bytes);
+        return cudaSuccess;
+    }
+    void unreserve(int dev) {
+        void *dead = nullptr;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            Arena &a = arena[dev & 63];
+            if (!a.base) return;
+            if (a.live == 0) {
+                dead = a.base;
+                a = Arena();
+            } else {
+                a.released = true;                     // freed when its last block is returned
+            }
+        }
+        if (dead) cudaFree(dead);
+    }
+    void drain(int dev) {
+        std::multimap<size_t, void *> m;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            m.swap(blocks[dev & 63]);
+        }
+        for (auto &kv : m) cudaFree(kv.second);
+    }
+};
+static DevPool g_pool;
+
+static void pool_context_gone(int dev) {
+    bool last;
+    {
+        std::lock_guard<std::mutex> g(g_pool.mu);
+        last = --g_pool.contexts[dev & 63] <= 0;
+    }
+    if (last) {
+        g_pool.drain(dev);
+        g_pool.unreserve(dev);
+    }
+}
+
+static cudaError_t pool_alloc(void **out, size_t bytes, size_t *cap) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if ((*out = g_pool.take(dev, bytes, cap)) != nullptr) return cudaSuccess;
+    *cap = bytes;
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        g_pool.drain(dev);
+        e = cudaMalloc(out, bytes);
+    }
+    return e;
+}
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    size_t cap = 0;                            // bytes of the block behind p (>= n * sizeof(T))
+    int dev = 0;
     cudaError_t alloc(size_t count) {
+        if (p) cudaDeviceSynchronize();        // re-allocation: work in flight may still read the old block
         release();
         n = count;
         if (!count) return cudaSuccess;
-        return cudaMalloc(&p, count * sizeof(T));
+        cudaGetDevice(&dev);
+        return pool_alloc(reinterpret_cast<void **>(&p), count * sizeof(T), &cap);
     }
-    void release() {
-        if (p) cudaFree(p);
+    void release() {                           // the caller guarantees that no work in flight uses the block
+        if (p) g_pool.give(dev, p, cap);
         p = nullptr;
         n = 0;
     }
@@ -405,6 +570,14 @@ static int32_t upload_rows_expanded(qc_plan *pl, DevBuf<cd> &buf, const double *
     cudaStream_t st = pl->ctx->stream;
     if (batched) {
         QC_CUDA(cudaMemcpyAsync(buf.p, host, batch * row * sizeof(cd), cudaMemcpyHostToDevice, st));
+    } else if (batch * row <= (size_t)1 << 26) {
+        // up to 1 GiB: replicate on the host and copy (no kernel: see the note on zeros in qc_plan_create)
+        std::vector<cd> full(batch * row);
+        const cd *src = reinterpret_cast<const cd *>(host);
+        for (size_t b = 0; b < batch; ++b) memcpy(full.data() + b * row, src, row * sizeof(cd));
+        QC_CUDA(cudaMemcpyAsync(buf.p, full.data(), batch * row * sizeof(cd), cudaMemcpyHostToDevice, st));
+        QC_CUDA(cudaStreamSynchronize(st));
+        return QC_OK;
     } else {
         if (pl->tmp_row.n < row) QC_CUDA(pl->tmp_row.alloc(row));
         QC_CUDA(cudaMemcpyAsync(pl->tmp_row.p, host, row * sizeof(cd), cudaMemcpyHostToDevice, st));
@@ -451,6 +624,10 @@ extern "C" int32_t qc_create(int32_t device, void *stream, qc_context **out) {
     }
     QC_CUDA(cudaEventCreate(&c->ev0));
     QC_CUDA(cudaEventCreate(&c->ev1));
+    {
+        std::lock_guard<std::mutex> g(g_pool.mu);
+        g_pool.contexts[device & 63]++;
+    }
     *out = c;
     return QC_OK;
 }
@@ -495,10 +672,33 @@ extern "C" int64_t qc_launch_count(qc_context *ctx) { return ctx ? ctx->launches
 extern "C" int32_t qc_mem_info(qc_context *ctx, int64_t *free_bytes, int64_t *total_bytes) {
     if (!ctx || !free_bytes || !total_bytes) return fail(QC_ERR_ARG, "qc_mem_info: NULL argument");
     QC_CUDA(cudaSetDevice(ctx->device));
+    g_pool.drain(ctx->device);                 // cached blocks are free memory
     size_t f = 0, t = 0;
     QC_CUDA(cudaMemGetInfo(&f, &t));
     *free_bytes = (int64_t)f;
     *total_bytes = (int64_t)t;
+    return QC_OK;
+}
+
+extern "C" int32_t qc_pool_reserve(qc_context *ctx, int64_t bytes) {
+    if (!ctx || bytes < 0) return fail(QC_ERR_ARG, "qc_pool_reserve: bad argument");
+    QC_CUDA(cudaSetDevice(ctx->device));
+    if (bytes == 0) {
+        g_pool.unreserve(ctx->device);
+        return QC_OK;
+    }
+    g_pool.drain(ctx->device);
+    const cudaError_t e = g_pool.reserve(ctx->device, (size_t)bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(QC_ERR_NOMEM, "qc_pool_reserve: %lld bytes: %s", (long long)bytes, cudaGetErrorString(e));
+    }
+    return QC_OK;
+}
+
+extern "C" int32_t qc_sm_count(qc_context *ctx, int32_t *sm_count) {
+    if (!ctx || !sm_count) return fail(QC_ERR_ARG, "qc_sm_count: NULL argument");
+    *sm_count = ctx->sm_count;
     return QC_OK;
 }
 
@@ -584,9 +784,17 @@ extern "C" int32_t qc_plan_create(qc_context *ctx, const qc_plan_desc *desc, qc_
         cudaGetLastError();
         return rc;
     }
-    QC_CUDA(cudaMemsetAsync(pl->E_base.p, 0, pl->E_base.n * sizeof(cd), ctx->stream));
-    QC_CUDA(cudaMemsetAsync(pl->E_out.p, 0, pl->E_out.n * sizeof(cd), ctx->stream));
-    QC_CUDA(cudaMemsetAsync(pl->a0.p, 0, pl->a0.n * sizeof(cd), ctx->stream));
+    {
+        // zeros by copy, not by cudaMemset: a memset is a kernel, and while another plan's sweep holds every SM (one CTA
+        // per SM for a whole sweep) a kernel of this stream -- and every copy queued behind it -- waits for a CTA to
+        // retire; plan set-up runs beside the propagation of the previous sub-batch (newcheb.run_variants)
+        const size_t nz = std::max(pl->E_base.n, std::max(pl->E_out.n, pl->a0.n));
+        std::vector<cd> zeros(nz, qc::cmk(0.0, 0.0));
+        QC_CUDA(cudaMemcpyAsync(pl->E_base.p, zeros.data(), pl->E_base.n * sizeof(cd), cudaMemcpyHostToDevice, ctx->stream));
+        QC_CUDA(cudaMemcpyAsync(pl->E_out.p, zeros.data(), pl->E_out.n * sizeof(cd), cudaMemcpyHostToDevice, ctx->stream));
+        if (pl->a0.n) QC_CUDA(cudaMemcpyAsync(pl->a0.p, zeros.data(), pl->a0.n * sizeof(cd), cudaMemcpyHostToDevice, ctx->stream));
+        QC_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     if (grid) {
         std::vector<cd> t1, t2;
         fill_twiddles(pl->log2n, t1, t2);

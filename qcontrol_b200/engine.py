@@ -82,6 +82,16 @@ class Context:
         check(lib.qc_mem_info(self._h, C.byref(f), C.byref(t)))
         return int(f.value), int(t.value)
 
+    @property
+    def sm_count(self) -> int:
+        n = C.c_int32()
+        check(lib.qc_sm_count(self._h, C.byref(n)))
+        return int(n.value)
+
+    def pool_reserve(self, nbytes: int):
+        """Reserve an arena of device memory for the plans of this device (0 gives it back), see qc_pool_reserve."""
+        check(lib.qc_pool_reserve(self._h, int(nbytes)))
+
     def fp64_peak_tflops(self) -> float:
         tf = C.c_double()
         check(lib.qc_measure_fp64_peak(self._h, C.byref(tf)))

@@ -24,6 +24,7 @@ from types import SimpleNamespace
 import numpy
 
 from . import batch as qbatch
+from . import config as qconfig
 from . import control, engine as _eng, math_base, phys_base, reporter, task_manager
 from .config import ReportPlotRootConfiguration, ReportRootConfiguration, ReportTableRootConfiguration, TaskRootConfiguration
 
@@ -175,22 +176,38 @@ def memory_chunks(confs, idxs, free_bytes, fraction=0.8):
     return chunks
 
 
+def pipeline_pieces(chunk, np_, sm_count, grid):
+    """Cut a memory-sized sub-batch of a GRID shape into pieces of whole waves so that the host set-up of the next piece
+    (task_manager.create, step-scalar and Newton tables, plan allocation and upload) runs on a second thread and a
+    second stream while the GPU propagates the current one.  A piece is two waves of CTAs of kernel A (one run per
+    CTA at np = 2048, two at 1024, four below, a two-CTA cluster per run at 4096); N-level batches are not cut -- kernel
+    B wants as many runs per launch as it can get (kernel B)."""
+    if not grid:
+        return [chunk]
+    runs_per_wave = sm_count * (4 if np_ <= 512 else 2 if np_ == 1024 else 1) // (2 if np_ >= 4096 else 1)
+    piece = 2 * max(runs_per_wave, 1)
+    if len(chunk) < 2 * piece:
+        return [chunk]
+    return [chunk[k:k + piece] for k in range(0, len(chunk), piece)]
+
+
 def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True, timings=None):
     """Expand -> configure -> shard -> batched GPU runs -> per-run tables.  Returns {run index: rows}.
     ``timings`` (a dict, optional) receives the wall-clock split of this rank: configuration, per-run task set-up
     (task_manager.create + report set-up), plan set-up (tables of step scalars, Newton tables, uploads), the control
-    loops themselves, and reporting."""
-    import contextlib
-    import io
+    loops themselves, and reporting.  Set-up of piece k + 1 overlaps the control loops of piece k (one producer
+    thread, two contexts = two streams on the same device); ``setup_wait_s`` is the part of it the GPU waited for."""
+    import concurrent.futures
     import time
-    tm_ = {"config_s": 0.0, "task_setup_s": 0.0, "plan_setup_s": 0.0, "run_s": 0.0, "report_s": 0.0, "plans": 0}
+    tm_ = {"config_s": 0.0, "task_setup_s": 0.0, "plan_setup_s": 0.0, "setup_wait_s": 0.0, "run_s": 0.0, "report_s": 0.0,
+           "plans": 0}
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0")) if device is None else device
     t_mark = time.perf_counter()
     confs, costs, shapes = [], [], []
     for i, data_task in enumerate(variants):
-        with contextlib.redirect_stdout(io.StringIO()):
+        with qconfig.quiet():
             conf = TaskRootConfiguration()
             conf.load(data_task)
         validate(conf)
@@ -201,20 +218,27 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True, 
                        bool(conf.fitter.hf_hide), conf.task_type, float(conf.L), float(conf.fitter.propagation.m)))
     mine = qbatch.lpt_shards(costs, world)[rank]
     results = {}
-    ctx = _eng.Context(local)
+    ctxs = [_eng.Context(local), _eng.Context(local)]       # piece k runs on ctxs[k % 2] while piece k + 1 is set up on the other
     OT = ReportRootConfiguration.ReportFitterConfiguration.OutputType
     tm_["config_s"] = time.perf_counter() - t_mark
     work = []
+    sm_count = ctxs[0].sm_count
     for shape, group in qbatch.plan_groups(shapes, mine).items():
         try:
-            work += memory_chunks(confs, group, ctx.mem_info()[0])
+            # two plans are alive at a time (the running piece and the one being set up): 40 % of the free memory each
+            for chunk in memory_chunks(confs, group, ctxs[0].mem_info()[0], fraction=0.4):
+                c0 = confs[chunk[0]]
+                work += pipeline_pieces(chunk, int(c0.np), sm_count, c0.hamil_type == TaskRootConfiguration.HamilType.NTRIV)
         except MemoryError as e:
             print("An exception interrupted the jobs %s: %s" % (group, e), file=sys.stderr)
-    for idxs in work:
-        t_mark = time.perf_counter()
+
+    def prepare(k):
+        """Host set-up of piece k (producer thread): per-run tasks and reporters, then the plan on this piece's context."""
+        idxs, ctx = work[k], ctxs[k % 2]
+        t0 = time.perf_counter()
         pbs, reps = [], []
         for i in idxs:
-            with contextlib.redirect_stdout(io.StringIO()):
+            with qconfig.quiet():
                 tm = task_manager.create(confs[i])
                 rep_json = resolve_input_templates(variants[i], copy.deepcopy(data_rep))
                 ct, cp = ReportTableRootConfiguration(), ReportPlotRootConfiguration()
@@ -223,12 +247,42 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True, 
             print_input(ct.fitter.out_path, confs[i], "table_inp_-1.txt")
             reps.append(reporter.MultipleFitterReporter(ct.fitter, cp.fitter).open())
             pbs.append(problem_from(confs[i], tm))
-        tm_["task_setup_s"] += time.perf_counter() - t_mark
-        t_mark = time.perf_counter()
+        t1 = time.perf_counter()
         grid = pbs[0].hamil == "ntriv"
         b = (control.GridBatch if grid else control.NLevelBatch)(pbs, ctx=ctx)
-        tm_["plan_setup_s"] += time.perf_counter() - t_mark
+        return idxs, pbs, reps, b, grid, t1 - t0, time.perf_counter() - t1
+
+    # Fresh device memory is expensive beside a running sweep (an allocation by the driver returns only when the sweep
+    # ends): while the GPU is still idle, reserve the working set of the pipeline -- two plans are alive at a time --
+    # as an arena of the library (qc_pool_reserve); it goes back when the last piece is done.
+    reserved = False
+    if len(work) > 1:
+        need = 0
+        for idxs in work:
+            c0 = confs[idxs[0]]
+            grid = c0.hamil_type == TaskRootConfiguration.HamilType.NTRIV
+            nt_max = max(int(confs[i].fitter.propagation.nt) for i in idxs)
+            need = max(need, _eng.plan_footprint(_eng.HAMIL_NONTRIV if grid else _eng.HAMIL_BH_X, c0.np, c0.nlevs, c0.nb,
+                                                 c0.fitter.propagation.nch, len(idxs), nt_max,
+                                                 bool(c0.fitter.hf_hide) and grid, _NAMES.get(c0.task_type) in control.TRAJ_TASKS))
+        want = int(2.1 * need) + (64 << 20)
+        if want <= 0.9 * ctxs[0].mem_info()[0]:
+            try:
+                ctxs[0].pool_reserve(want)
+                reserved = True
+            except Exception:
+                reserved = False
+    pool = concurrent.futures.ThreadPoolExecutor(1)
+    nxt = pool.submit(prepare, 0) if work else None
+    for k in range(len(work)):
+        t_mark = time.perf_counter()
+        idxs, pbs, reps, b, grid, t_task, t_plan = nxt.result()
+        tm_["setup_wait_s"] += time.perf_counter() - t_mark
+        tm_["task_setup_s"] += t_task
+        tm_["plan_setup_s"] += t_plan
         tm_["plans"] += 1
+        nxt = pool.submit(prepare, k + 1) if k + 1 < len(work) else None
+        ctx = ctxs[k % 2]
         t_mark = time.perf_counter()
         if any(r.conf_rep_table.plotting_flag in (OT.ALL, OT.TABLES) for r in reps):
             # per-step tables were asked for: instrument the resident states at the steps the tables keep
@@ -257,20 +311,24 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True, 
         t_mark = time.perf_counter()
         if b.observer is not None:
             b.observer.close()
-        for k, i in enumerate(idxs):
-            results[i] = hist[k]
-            for r in hist[k]:
-                reps[k].print_iter_point_fitter(r.it, r.goal_close, None if r.E_tlist is None else list(r.E_tlist),
-                                                pbs[k].t_list, numpy.complex128(r.Fsm), numpy.float64(r.E_int), r.J,
-                                                pbs[k].nt)
-            reps[k].close()
-            if errors[k] and verbose:
-                print("An exception interrupted the job #%d: %s" % (i, errors[k]), file=sys.stderr)
+        for j, i in enumerate(idxs):
+            results[i] = hist[j]
+            for r in hist[j]:
+                reps[j].print_iter_point_fitter(r.it, r.goal_close, None if r.E_tlist is None else list(r.E_tlist),
+                                                pbs[j].t_list, numpy.complex128(r.Fsm), numpy.float64(r.E_int), r.J,
+                                                pbs[j].nt)
+            reps[j].close()
+            if errors[j] and verbose:
+                print("An exception interrupted the job #%d: %s" % (i, errors[j]), file=sys.stderr)
             elif verbose:
                 print("Job #%d is done" % i)
         b.close()
         tm_["report_s"] += time.perf_counter() - t_mark
-    ctx.close()
+    pool.shutdown()
+    if reserved:
+        ctxs[0].pool_reserve(0)
+    for ctx in ctxs:
+        ctx.close()
     if timings is not None:
         timings.update(tm_)
     return results

@@ -292,3 +292,20 @@ def test_shared_reciprocal_quotient_is_correctly_rounded():
         q2 = float(Fraction(q) + Fraction(r) * Fraction(rb))        # fma(r, rb, q): one rounding
         bad += q2 != x / y
     assert bad == 0
+
+
+def test_pipeline_pieces_cut_whole_waves():
+    """newcheb.pipeline_pieces: a big grid sub-batch becomes pieces of two waves of CTAs (so that the set-up of the next
+    piece can run beside the propagation of the current one), every run exactly once and in order; small batches and
+    N-level batches stay whole."""
+    from qcontrol_b200 import newcheb
+    chunk = list(range(1024))
+    pieces = newcheb.pipeline_pieces(chunk, 2048, 148, True)
+    assert [len(p) for p in pieces] == [296, 296, 296, 136]
+    assert sum(pieces, []) == chunk
+    assert newcheb.pipeline_pieces(chunk, 1024, 148, True) == [chunk]            # fewer than two pieces of 592
+    assert [len(p) for p in newcheb.pipeline_pieces(chunk + chunk, 1024, 148, True)] == [592, 592, 592, 272]
+    assert newcheb.pipeline_pieces(chunk, 512, 148, True) == [chunk]             # fewer than two pieces of 1184
+    assert [len(p) for p in newcheb.pipeline_pieces(chunk, 4096, 148, True)] == [148] * 6 + [136]
+    assert newcheb.pipeline_pieces(chunk, 1, 148, False) == [chunk]              # kernel B: as many runs per launch as possible
+    assert newcheb.pipeline_pieces(list(range(500)), 2048, 148, True) == [list(range(500))]
