@@ -303,9 +303,9 @@ def test_pipeline_pieces_cut_whole_waves():
     pieces = newcheb.pipeline_pieces(chunk, 2048, 148, True)
     assert [len(p) for p in pieces] == [296, 296, 296, 136]
     assert sum(pieces, []) == chunk
-    assert newcheb.pipeline_pieces(chunk, 1024, 148, True) == [chunk]            # fewer than two pieces of 592
-    assert [len(p) for p in newcheb.pipeline_pieces(chunk + chunk, 1024, 148, True)] == [592, 592, 592, 272]
-    assert newcheb.pipeline_pieces(chunk, 512, 148, True) == [chunk]             # fewer than two pieces of 1184
+    assert [len(p) for p in newcheb.pipeline_pieces(chunk, 1024, 148, True)] == [592, 432]
+    assert newcheb.pipeline_pieces(chunk, 512, 148, True) == [chunk]             # one piece of 1184 holds them all
     assert [len(p) for p in newcheb.pipeline_pieces(chunk, 4096, 148, True)] == [148] * 6 + [136]
     assert newcheb.pipeline_pieces(chunk, 1, 148, False) == [chunk]              # kernel B: as many runs per launch as possible
-    assert newcheb.pipeline_pieces(list(range(500)), 2048, 148, True) == [list(range(500))]
+    assert [len(p) for p in newcheb.pipeline_pieces(list(range(500)), 2048, 148, True)] == [296, 204]
+    assert newcheb.pipeline_pieces(list(range(296)), 2048, 148, True) == [list(range(296))]
