@@ -309,6 +309,49 @@ def test_memory_sized_sub_batches(ctx):
     assert used >= 0.5 * est
 
 
+def test_device_block_pool_and_arena(ctx, golden):
+    """The library's device memory management behind the pipelined batch entry point: (1) blocks given back by
+    qc_plan_destroy are cached and returned to the driver by qc_mem_info; (2) qc_pool_reserve cuts later plans from one
+    arena -- no driver allocation -- and a plan living in the arena computes bit for bit what a plan outside computes,
+    although its memory is recycled, not fresh; (3) an arena given back while a plan still lives in it is freed when that
+    plan goes."""
+    from qcontrol_b200 import engine, math_base
+    slack = 96 << 20
+    free0 = ctx.mem_info()[0]
+    pl = engine.Plan(ctx, engine.HAMIL_NONTRIV, 1024, 2, 1, 64, 64, 2000, hf_hide=True, store_traj=True)      # ~ 4.2 GB
+    assert free0 - ctx.mem_info()[0] > (3 << 30)
+    pl.close()
+    assert abs(ctx.mem_info()[0] - free0) <= slack                     # cached blocks count as free and are drained
+
+    g = golden("one_step_krotov")
+    n, nch = g["v"].shape[1], int(g["nch"])
+    xp, dv = math_base.newton_table(nch, float(g["t_sc"]))
+
+    def one_step():
+        q = engine.Plan(ctx, engine.HAMIL_NONTRIV, n, 2, 1, nch, 3, 4)
+        q.set_static(g["v"], np.ascontiguousarray(g["akx2"].real), None, float(g["dx"]))
+        q.set_poly(0, xp, dv, float(g["emin"]), float(g["emax"]), float(g["t_sc"]), float(g["eL"]))
+        q.set_state(np.stack([g["psi_in"][None]] * 3))
+        q.prop_step(0, np.full(3, float(np.real(g["E_f"]))))
+        return q, q.get_state()
+
+    q, outside = one_step()
+    q.close()
+    ctx.pool_reserve(1 << 30)
+    reserved = ctx.mem_info()[0]
+    assert free0 - reserved >= (1 << 30) - slack
+    dirty = engine.Plan(ctx, engine.HAMIL_NONTRIV, 1024, 2, 1, 64, 16, 200, hf_hide=True, store_traj=True)     # leaves its bytes behind
+    dirty.set_state(np.full(dirty.state_shape, 7.0 + 3.0j))
+    dirty.close()
+    q, inside = one_step()
+    assert abs(ctx.mem_info()[0] - reserved) <= (8 << 20)                 # served from the arena, nothing from the driver
+    assert np.array_equal(inside, outside)
+    ctx.pool_reserve(0)                                                   # a plan still lives in the arena: deferred
+    assert abs(ctx.mem_info()[0] - reserved) <= (8 << 20)
+    q.close()
+    assert abs(ctx.mem_info()[0] - free0) <= slack
+
+
 def test_truncated_series_is_opt_in_and_within_its_bound(ctx, golden, monkeypatch):
     """OPT-IN truncation of the interpolation series (qc_set_poly_orders, control.GridBatch(poly_tol=...)): off by
     default -- the plain path sums all nch terms like the reference --; with a per-step bound of 1e-11 the orders drop
