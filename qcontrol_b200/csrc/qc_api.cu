@@ -17,6 +17,7 @@
 #include "../../include/qcontrol_b200.h"
 #include "qc_grid.cuh"
 #include "qc_grid8.cuh"
+#include "qc_grid8x2.cuh"
 #include "qc_grid2d.cuh"
 #include "qc_nlevel.cuh"
 
@@ -555,6 +556,22 @@ static void fill_twiddles8(std::vector<cd> &t) {
         for (int n = 0; n < 4; ++n) t.push_back(root(k3 * n, 32));
 }
 
+// ... and of its np = 1024 sibling (qc_grid8x2.cuh)
+static void fill_twiddles8x2(std::vector<cd> &t) {
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    auto root = [&](int m, int M) {
+        const long double ang = -two_pi * (long double)(m % M) / (long double)M;
+        return qc::cmk((double)cosl(ang), (double)sinl(ang));
+    };
+    t.clear();
+    for (int k1 = 0; k1 < 8; ++k1)
+        for (int T = 0; T < 128; ++T) t.push_back(root(k1 * T, 1024));
+    for (int k2 = 0; k2 < 8; ++k2)
+        for (int m = 0; m < 16; ++m) t.push_back(root(k2 * m, 128));
+    for (int k3 = 0; k3 < 4; ++k3)
+        for (int n = 0; n < 4; ++n) t.push_back(root(k3 * n, 16));
+}
+
 template <typename T>
 static int32_t upload(qc_plan *pl, DevBuf<T> &buf, const void *host, size_t count) {
     if (buf.n != count) QC_CUDA(buf.alloc(count));
@@ -800,9 +817,9 @@ extern "C" int32_t qc_plan_create(qc_context *ctx, const qc_plan_desc *desc, qc_
         fill_twiddles(pl->log2n, t1, t2);
         int32_t rc = upload(pl, pl->tw1, t1.data(), t1.size());
         if (rc == QC_OK) rc = upload(pl, pl->tw2, t2.data(), t2.size());
-        if (rc == QC_OK && pl->log2n == 11) {
+        if (rc == QC_OK && (pl->log2n == 11 || pl->log2n == 10)) {
             std::vector<cd> t8;
-            fill_twiddles8(t8);
+            if (pl->log2n == 11) fill_twiddles8(t8); else fill_twiddles8x2(t8);
             rc = upload(pl, pl->tw8, t8.data(), t8.size());
         }
         if (rc != QC_OK) {
@@ -1033,6 +1050,20 @@ static int32_t launch_grid8(qc_plan *pl, const qc::GridParams &gp, cudaStream_t 
     return QC_OK;
 }
 
+static int32_t launch_grid8x2(qc_plan *pl, const qc::GridParams &gp, cudaStream_t stream) {
+    typedef qc::Grid8x2Cfg C;
+    static bool attr_done[64] = {false};
+    const int dev = pl->ctx->device;
+    if (!attr_done[dev & 63]) {
+        QC_CUDA(cudaFuncSetAttribute(qc::grid8x2_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+        attr_done[dev & 63] = true;
+    }
+    qc::grid8x2_sweep_kernel<<<(gp.run_count + 1) / 2, C::NTHREADS, C::SMEM_BYTES, stream>>>(gp);
+    pl->ctx->launches++;
+    QC_CUDA(cudaGetLastError());
+    return QC_OK;
+}
+
 template <int NL>
 static int32_t launch_nlevel(qc_plan *pl, const qc::NLevelParams &np_) {
     const int threads = 128;
@@ -1149,6 +1180,9 @@ static int32_t run_sweep(qc_plan *pl, const qc_sweep_args *a, bool single_step, 
             case 8: return launch_grid<8>(pl, g, lst);
             case 9: return launch_grid<9>(pl, g, lst);
             case 10:
+                // 512-thread form, two runs per CTA (qc_grid8x2.cuh): sweeps of the prescribed / Krotov field laws
+                if (var == 2 && !single_step && !ap.cplx && !ap.active && mode <= QC_FIELD_KROTOV_BWD)
+                    return launch_grid8x2(pl, g, lst);
                 // two runs per CTA with the tensor-memory hand-over once the batch fills every SM anyway (the plain
                 // form holds two one-run CTAs per SM: same residency, 20 % more shared-memory traffic)
                 {
