@@ -43,6 +43,10 @@
 #include "qc_fft.cuh"
 #include "qc_local.cuh"
 
+#ifndef QC_CL_LATE_ARRIVE
+#define QC_CL_LATE_ARRIVE 2
+#endif
+
 namespace qc {
 
 struct GridParams {
@@ -593,13 +597,18 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
             if (NAMED && !TMH) bar_arrive(BAR_FULL_OWN + par, HN);   // producer side of a named barrier (no fence needed)
             // cluster form: one split-phase cluster barrier per order is the whole protocol -- the partner waits for
             // it before reading, and since the buffers alternate, this level's wait of order j+1 already implies
-            // that the partner has finished reading buffer `par` of order j
-            if (CL) cl_arrive();
+            // that the partner has finished reading buffer `par` of order j.  The arrive has RELEASE semantics (SASS:
+            // MEMBAR.ALL.GPU): it waits until the remote stores above have landed in the partner's shared memory, so it
+            // is issued behind the forward transform, when they have (right after the stores it cost 20 % of the warp
+            // time in the memory-barrier stall: np = 4096 0.39 -> 0.42 of the FP64 peak, profiles/r02z_*, r02ab_*); the
+            // partner needs it an order later.
+            if (CL && !QC_CL_LATE_ARRIVE) cl_arrive();
             // pass 1 : DFT over n1, twiddle w_N^(k1*t), transpose
             {
                 TmemTwiddles tw(t_tw1);
                 dft16_table_out<false>(a, tw, [&](int k1, cd val) { bufA[k1 * S1 + t] = val; });
             }
+            if (CL && QC_CL_LATE_ARRIVE == 1) cl_arrive();
             if (TMH && !RDV) {
                 // hand-over through tensor memory: the asynchronous stores of phi have long landed behind the
                 // butterflies of pass 1; make them visible to the partner warp and signal "phi of this parity is there"
@@ -626,6 +635,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
 #pragma unroll
                 for (int q = 0; q < Q; ++q) dft<R3, false>(a + q * R3);
             }
+            if (CL && QC_CL_LATE_ARRIVE == 2) cl_arrive();
             // k-space: kinetic multiplier (with c1 and the 1/N of the inverse transform folded in)
             if (!ILV) {
 #pragma unroll
