@@ -43,6 +43,9 @@
 #include "qc_fft.cuh"
 #include "qc_local.cuh"
 
+#ifndef QC_RDV_MBAR
+#define QC_RDV_MBAR 1
+#endif
 #ifndef QC_CL_LATE_ARRIVE
 #define QC_CL_LATE_ARRIVE 2
 #endif
@@ -166,6 +169,9 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
                      (uint32_t)__cvta_generic_to_shared(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(b)
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
@@ -388,10 +394,15 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
     // ids and one for sums).  A "phi has been read" handshake is not needed: the buffers alternate with the order
     // parity, and a level passes its wait for the partner's order j+1 only after the partner has finished order j.
     // TMP: seven per run (two level barriers, four "available" ids, one for sums).  RDV (TMP with a level per warp,
-    // np = 512, four runs per CTA): a run is two warps, and 4 x 5 ids would not fit the 15 a CTA has, so the hand-over
-    // is a symmetric rendezvous of the two warps once per order (id 1 + RPC + rslot) -- the double-buffered phi in
-    // tensor memory still lets either warp run ahead into the transform of the next order
+    // np = 512, four runs per CTA): a run is two warps, and 4 x 5 ids would not fit the 15 a CTA has, so the four
+    // "available" signals of a run are MBARRIERS in shared memory (32 arrivals each: every lane of the producer warp
+    // arrives once its own tensor-memory stores have completed; the consumer warp spins on the phase parity) -- the
+    // same one-order slack as the named barriers of the other forms.  (QC_RDV_MBAR = 0: the symmetric rendezvous of
+    // the two warps once per order on one named barrier, the first version of this form.)
     constexpr bool RDV = TMP && WPL == 1;
+    constexpr bool RDVM = RDV && QC_RDV_MBAR;
+    uint64_t *s_hb = reinterpret_cast<uint64_t *>(smem_raw + (PK ? RPC * C::RUN_BYTES + 64 : 0)) + 4 * rslot;   // [lev][parity]
+    uint32_t hb_use0 = 0, hb_use1 = 0;            // completed waits on the partner's barrier of parity 0 / 1
     const int bar_run = RDV ? 1 + rslot : TMP ? 1 + 7 * rslot + 6 : PKL ? 1 + 5 * rslot + 4 : 1 + rslot;
     const int bar_full = TMP ? 1 + 7 * rslot + 2 : PKL ? 1 + 5 * rslot : 3;
     const int bar_rdv = 1 + RPC + rslot;
@@ -448,6 +459,10 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
     }
     // ---- tensor memory: one warp allocates, everybody learns the base address ------------------------
     uint32_t *s_tmem = PK ? reinterpret_cast<uint32_t *>(smem_raw + RPC * C::RUN_BYTES) : reinterpret_cast<uint32_t *>(s_red + 30);
+    if (RDVM && tid == 32) {
+        uint64_t *hb = reinterpret_cast<uint64_t *>(smem_raw + RPC * C::RUN_BYTES + 64);
+        for (int i = 0; i < 4 * RPC; ++i) mbar_init(hb + i, 32);
+    }
     if (tid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          (uint32_t)__cvta_generic_to_shared(s_tmem)),
@@ -609,12 +624,13 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
                 dft16_table_out<false>(a, tw, [&](int k1, cd val) { bufA[k1 * S1 + t] = val; });
             }
             if (CL && QC_CL_LATE_ARRIVE == 1) cl_arrive();
-            if (TMH && !RDV) {
+            if (TMH && (!RDV || RDVM)) {
                 // hand-over through tensor memory: the asynchronous stores of phi have long landed behind the
                 // butterflies of pass 1; make them visible to the partner warp and signal "phi of this parity is there"
                 tmem_wait_st();
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                bar_arrive(BAR_FULL_OWN + par, HN);
+                if (RDVM) mbar_arrive(s_hb + 2 * lev + par);
+                else bar_arrive(BAR_FULL_OWN + par, HN);
             }
             level_sync();                                                           // (#1)
 #pragma unroll
@@ -683,7 +699,10 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
             // pointwise part (hamil_2d.py:60-71, phys_base.py:98-111) and accumulation (phys_base.py:170-172),
             // in chunks of four grid points: psi and own phi from TMEM, the other level's phi from shared memory
             if (NAMED && !RDV) bar_sync(BAR_FULL_OTH + par, HN);
-            if (RDV) {
+            if (RDVM) {
+                if (par == 0) mbar_wait(s_hb + 2 * (1 - lev), hb_use0++ & 1u);
+                else mbar_wait(s_hb + 2 * (1 - lev) + 1, hb_use1++ & 1u);
+            } else if (RDV) {
                 tmem_wait_st();
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 bar_sync(bar_rdv, HN);
