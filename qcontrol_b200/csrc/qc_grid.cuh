@@ -46,6 +46,9 @@
 #ifndef QC_RDV_MBAR
 #define QC_RDV_MBAR 1
 #endif
+#ifndef QC_TMH_MBAR
+#define QC_TMH_MBAR 0
+#endif
 #ifndef QC_CL_LATE_ARRIVE
 #define QC_CL_LATE_ARRIVE 2
 #endif
@@ -400,8 +403,13 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
     // same one-order slack as the named barriers of the other forms.  (QC_RDV_MBAR = 0: the symmetric rendezvous of
     // the two warps once per order on one named barrier, the first version of this form.)
     constexpr bool RDV = TMP && WPL == 1;
-    constexpr bool RDVM = RDV && QC_RDV_MBAR;
-    uint64_t *s_hb = reinterpret_cast<uint64_t *>(smem_raw + (PK ? RPC * C::RUN_BYTES + 64 : 0)) + 4 * rslot;   // [lev][parity]
+    // QC_TMH_MBAR = 1 (diagnostic): the same mbarriers (TPL arrivals each) in the other tensor-memory hand-over forms
+    // instead of the named barriers, whose bar.sync also makes the consumer warps of a level wait for each other --
+    // measured neutral at np = 2048 (prescribed 0.616 / 0.615, Krotov forward 0.602 / 0.611) and worse at np = 1024
+    // (0.591 / 0.621), so the named barriers stay
+    constexpr bool RDVM = TMH && (RDV ? QC_RDV_MBAR : QC_TMH_MBAR);
+    uint64_t *s_hb = PK ? reinterpret_cast<uint64_t *>(smem_raw + RPC * C::RUN_BYTES + 64) + 4 * rslot
+                        : reinterpret_cast<uint64_t *>(s_red + 24);                                 // [lev][parity]
     uint32_t hb_use0 = 0, hb_use1 = 0;            // completed waits on the partner's barrier of parity 0 / 1
     const int bar_run = RDV ? 1 + rslot : TMP ? 1 + 7 * rslot + 6 : PKL ? 1 + 5 * rslot + 4 : 1 + rslot;
     const int bar_full = TMP ? 1 + 7 * rslot + 2 : PKL ? 1 + 5 * rslot : 3;
@@ -460,8 +468,8 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
     // ---- tensor memory: one warp allocates, everybody learns the base address ------------------------
     uint32_t *s_tmem = PK ? reinterpret_cast<uint32_t *>(smem_raw + RPC * C::RUN_BYTES) : reinterpret_cast<uint32_t *>(s_red + 30);
     if (RDVM && tid == 32) {
-        uint64_t *hb = reinterpret_cast<uint64_t *>(smem_raw + RPC * C::RUN_BYTES + 64);
-        for (int i = 0; i < 4 * RPC; ++i) mbar_init(hb + i, 32);
+        uint64_t *hb = PK ? reinterpret_cast<uint64_t *>(smem_raw + RPC * C::RUN_BYTES + 64) : reinterpret_cast<uint64_t *>(s_red + 24);
+        for (int i = 0; i < 4 * (PK ? RPC : 1); ++i) mbar_init(hb + i, TPL);
     }
     if (tid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -698,7 +706,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
             }
             // pointwise part (hamil_2d.py:60-71, phys_base.py:98-111) and accumulation (phys_base.py:170-172),
             // in chunks of four grid points: psi and own phi from TMEM, the other level's phi from shared memory
-            if (NAMED && !RDV) bar_sync(BAR_FULL_OTH + par, HN);
+            if (NAMED && !RDV && !RDVM) bar_sync(BAR_FULL_OTH + par, HN);
             if (RDVM) {
                 if (par == 0) mbar_wait(s_hb + 2 * (1 - lev), hb_use0++ & 1u);
                 else mbar_wait(s_hb + 2 * (1 - lev) + 1, hb_use1++ & 1u);
