@@ -452,6 +452,19 @@ class GridBatch(_BatchBase):
         rows, _ = self._finish_forward(0, [f[0] for f in fields])
         return [[r] for r in rows]
 
+    def prewarm(self):
+        """Host tables the control loop needs before its first sweep (the padded prescribed field of iteration 0, the
+        carrier at T), computed ahead of time: newcheb.run_variants calls this on its set-up thread, beside the sweeps
+        of the previous sub-batch, so that the GPU does not idle while they are evaluated."""
+        if getattr(self.pbs[0], "task_type", "") == "optimal_control_krotov":
+            self._prewarm_krotov()
+        return self
+
+    def _prewarm_krotov(self):
+        self._E_presc_fwd = self._pad([self._prescribed_field(p, FORWARD) for p in self.pbs])
+        self._sqrt_hf_T = np.array([np.complex128(cmath.sqrt(p.laser_field_hf(np.float64(1.0), p.T, p.pcos, p.w_list)))
+                                    for p in self.pbs])
+
     def run_krotov(self, iter_max=None):
         """optimal_control_krotov for every run (fitter.py:441-489, 537-569).  All runs iterate in
         lock step; a run that has converged keeps its rows and is simply not reported further."""
@@ -460,8 +473,9 @@ class GridBatch(_BatchBase):
         done = np.zeros(self.B, bool)
         F_mid_1 = np.zeros(self.B)
         self.errors = [""] * self.B
-        sqrt_hf_T = np.array([np.complex128(cmath.sqrt(p.laser_field_hf(np.float64(1.0), p.T, p.pcos, p.w_list)))
-                              for p in self.pbs])
+        if getattr(self, "_sqrt_hf_T", None) is None:
+            self._prewarm_krotov()
+        sqrt_hf_T = self._sqrt_hf_T
         it = 0
         E_start = [self._prescribed_field(p, FORWARD)[0] for p in self.pbs]
         while True:
@@ -469,7 +483,7 @@ class GridBatch(_BatchBase):
             pl.snapshot_load(0)
             pl.record_state(0, 0, 0)                      # psi_tlist[0] = psi_init (fitter.py:227-229)
             if it == 0:
-                pl.set_E_base(self._pad([self._prescribed_field(p, FORWARD) for p in self.pbs]))
+                pl.set_E_base(self._E_presc_fwd)
                 self._sweep("iter_0f", FORWARD, (0, 1), 0, eng.FIELD_PRESCRIBED, 1, self.nt_max, -1, 0)
                 E0s = E_start
             else:

@@ -250,6 +250,8 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True, 
         t1 = time.perf_counter()
         grid = pbs[0].hamil == "ntriv"
         b = (control.GridBatch if grid else control.NLevelBatch)(pbs, ctx=ctx)
+        if grid:
+            b.prewarm()
         return idxs, pbs, reps, b, grid, t1 - t0, time.perf_counter() - t1
 
     # Fresh device memory is expensive beside a running sweep (an allocation by the driver returns only when the sweep
