@@ -49,6 +49,9 @@
 #ifndef QC_TMH_MBAR
 #define QC_TMH_MBAR 0
 #endif
+#ifndef QC_CL_SPLIT_PUSH
+#define QC_CL_SPLIT_PUSH 1
+#endif
 #ifndef QC_CL_LATE_ARRIVE
 #define QC_CL_LATE_ARRIVE 2
 #endif
@@ -610,10 +613,24 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
             const int par = j & 1;
             cd *stash = stash0 + par * N;
             const cd *stash_other = stash0_other + par * N;
+            // cluster form, QC_CL_SPLIT_PUSH: only the first four of the sixteen remote stores leave here; the others
+            // follow in three groups further down, re-read from the own copy in tensor memory, so that the slow
+            // distributed-shared-memory path never holds a queue of sixteen stores per thread (their source registers
+            // stay locked until the store has been taken: 12 % of the warp time in the long-scoreboard stall)
+            constexpr bool SPLIT = CL && QC_CL_SPLIT_PUSH;
             if (!ILV && !TMH) {
 #pragma unroll
-                for (int n1 = 0; n1 < 16; ++n1) stash[t + TPL * n1] = a[n1];
+                for (int n1 = 0; n1 < (SPLIT ? 4 : 16); ++n1) stash[t + TPL * n1] = a[n1];
             }
+            auto push_group = [&](int g) {
+                uint32_t rg[16];
+                cd v4[4];
+                tmem_ld16(t_phi + 16 * g, rg);
+                tmem_wait_ld();
+                tmem_unpack_c4(rg, v4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) stash[t + TPL * (4 * g + i)] = v4[i];
+            };
             const uint32_t t_phi_j = TMH ? t_phi + (uint32_t)(par * 64) : t_phi;
 #pragma unroll
             for (int c4 = 0; c4 < 16; c4 += 4) tmem_store_c4(t_phi_j + c4 * 4, a + c4);
@@ -632,6 +649,10 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
                 dft16_table_out<false>(a, tw, [&](int k1, cd val) { bufA[k1 * S1 + t] = val; });
             }
             if (CL && QC_CL_LATE_ARRIVE == 1) cl_arrive();
+            if (SPLIT) {
+                tmem_wait_st();
+                push_group(1);
+            }
             if (TMH && (!RDV || RDVM)) {
                 // hand-over through tensor memory: the asynchronous stores of phi have long landed behind the
                 // butterflies of pass 1; make them visible to the partner warp and signal "phi of this parity is there"
@@ -651,6 +672,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
                     TmemTwiddles tw(t_tw2);
                     dft16_table_out<false>(a, tw, [&](int k2, cd val) { bufA[k1p * S1 + pos2<R3, Q>(k2, n3p)] = val; });
                 }
+                if (SPLIT) push_group(2);
                 __syncwarp();
 #pragma unroll
                 for (int e = 0; e < 16; ++e)
@@ -659,7 +681,8 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
 #pragma unroll
                 for (int q = 0; q < Q; ++q) dft<R3, false>(a + q * R3);
             }
-            if (CL && QC_CL_LATE_ARRIVE == 2) cl_arrive();
+            if (SPLIT && R3 > 1) push_group(3);
+            if (CL && QC_CL_LATE_ARRIVE == 2 && !SPLIT) cl_arrive();
             // k-space: kinetic multiplier (with c1 and the 1/N of the inverse transform folded in)
             if (!ILV) {
 #pragma unroll
@@ -698,6 +721,7 @@ __global__ void __launch_bounds__(GridCfg<LOG2N, CL, RPC, ILV, VAR>::NTHREADS, 1
             if (R3 == 1) dft16<true>(a);
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) bufB[k1p * S1 + n2 * R3 + n3p] = a[n2];
+            if (SPLIT) cl_arrive();       // every group has long landed: the release fence finds nothing to wait for
             level_sync();                                                           // (#2)
             // inverse pass 1 -> kinetic term (already scaled by c1) at x = t + TPL*n1
             {
