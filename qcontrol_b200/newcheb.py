@@ -186,6 +186,8 @@ def pipeline_pieces(chunk, np_, sm_count, grid):
         return [chunk]
     runs_per_wave = sm_count * (4 if np_ <= 512 else 2 if np_ == 1024 else 1) // (2 if np_ >= 4096 else 1)
     piece = 2 * max(runs_per_wave, 1)
+    if os.environ.get("QC_PIPELINE_PIECE"):         # tests: any piece size; 0 = never cut
+        piece = int(os.environ["QC_PIPELINE_PIECE"]) or len(chunk)
     if len(chunk) <= piece:
         return [chunk]
     return [chunk[k:k + piece] for k in range(0, len(chunk), piece)]

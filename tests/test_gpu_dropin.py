@@ -227,6 +227,45 @@ def test_batch_entry_point(tmp_path):
         assert len(abs0) == pb.nt // 100 + 1
 
 
+def test_batch_entry_point_pipelined_pieces(tmp_path, monkeypatch):
+    """newcheb.run_variants with the batch cut into pieces (set-up of piece k + 1 on a second thread and stream beside
+    the control loops of piece k, plans cut from the arena of qc_pool_reserve): a template of 8 Krotov variants at
+    np = 256 in pieces of 3 (3 + 3 + 2, QC_PIPELINE_PIECE) must give exactly the tables of the uncut batch -- a run does
+    not depend on its position in a batch -- and those of the oracle."""
+    from qcontrol_b200 import batch, newcheb
+    dt = 350e-15 / 230000
+    nt = 60
+    T = dt * nt
+    tpl = {"task_type": "optimal_control_krotov", "pot_type": "morse", "wf_type": "morse", "hamil_type": "ntriv",
+           "init_guess": "gauss", "init_guess_hf": "exp", "nb": 1, "nlevs": 2, "T": T, "L": 5.0, "np": 256, "a": 1.0,
+           "De": 20000.0, "x0p": -0.17, "a_e": 1.0, "De_e": 10000.0, "Du": 20000.0,
+           "fitter": {"epsilon": 1e-8, "impulses_number": 1, "iter_max": 2, "h_lambda": 0.0066, "mod_log": 10 ** 9,
+                      "propagation": {"m": 0.5, "nch": 32, "nt": nt,
+                                      "E0": {"@SUBST:LIST": [2000.0, 2400.0, 2861.6, 3200.0]},
+                                      "t0": {"@SUBST:LIST": [T * 0.45, T * 0.55]},
+                                      "sigma": T / 6, "nu_L": 0.29297e15}}}
+    variants = batch.expand_substitutions(tpl)
+    assert len(variants) == 8
+    out = {}
+    for piece in ("0", "3"):
+        monkeypatch.setenv("QC_PIPELINE_PIECE", piece)
+        rep = {"fitter": {"out_path": str(tmp_path / ("p" + piece) / "E0={input:$.fitter.propagation.E0}_t0={input:$.fitter.propagation.t0}"),
+                          "plotting_flag": "tables_iter", "table.imin": -1}}
+        tm = {}
+        res = newcheb.run_variants(variants, rep, device=0, verbose=False, timings=tm)
+        assert tm["plans"] == (1 if piece == "0" else 3)
+        out[piece] = {i: np.array([[r.it, r.goal_close, r.Fsm, r.E_int, r.J] for r in rows]) for i, rows in res.items()}
+        assert sorted(out[piece]) == list(range(8))
+    for i in range(8):
+        assert out["0"][i].shape == out["3"][i].shape == (3, 5)
+        assert np.array_equal(out["0"][i], out["3"][i]), (i, out["0"][i] - out["3"][i])
+    for i in (0, 5, 7):
+        pb = qo.make_problem(copy.deepcopy(variants[i]))
+        rows = qo.Fitter(pb).run()
+        tab = np.array([[r.it, r.goal_close, r.Fsm, r.E_int, r.J] for r in rows])
+        assert np.allclose(out["3"][i], tab, rtol=1e-9, atol=1e-12), (i, out["3"][i] - tab)
+
+
 def test_newcheb_command_line(tmp_path):
     """`python -m qcontrol_b200.newcheb --json_task T.json --json_rep R.json` (newcheb.py:612-690): the reference's
     command line on a small substitution template; one output directory per variant, the summary table on stdout."""
