@@ -197,9 +197,12 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True, 
     """Expand -> configure -> shard -> batched GPU runs -> per-run tables.  Returns {run index: rows}.
     ``timings`` (a dict, optional) receives the wall-clock split of this rank: configuration, per-run task set-up
     (task_manager.create + report set-up), plan set-up (tables of step scalars, Newton tables, uploads), the control
-    loops themselves, and reporting.  Set-up of piece k + 1 overlaps the control loops of piece k (one producer
-    thread, two contexts = two streams on the same device); ``setup_wait_s`` is the part of it the GPU waited for."""
+    loops themselves, and reporting.  The set-up of later pieces overlaps the control loops of earlier ones (one
+    producer thread, QC_PIPELINE_RUNNERS = 1 runner thread, a context = stream per piece in flight): task / plan /
+    report times are sums over the pieces, ``setup_wait_s`` is what passed before the first sweep could start and
+    ``run_s`` the span from there to the end of the last control loop."""
     import concurrent.futures
+    import threading
     import time
     tm_ = {"config_s": 0.0, "task_setup_s": 0.0, "plan_setup_s": 0.0, "setup_wait_s": 0.0, "run_s": 0.0, "report_s": 0.0,
            "plans": 0}
@@ -220,45 +223,122 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True, 
                        bool(conf.fitter.hf_hide), conf.task_type, float(conf.L), float(conf.fitter.propagation.m)))
     mine = qbatch.lpt_shards(costs, world)[rank]
     results = {}
-    ctxs = [_eng.Context(local), _eng.Context(local)]       # piece k runs on ctxs[k % 2] while piece k + 1 is set up on the other
+    # Pipeline: ONE producer thread sets pieces up (tasks, reporters, plan upload), RUNNERS runner threads drive the
+    # control loops of consecutive pieces, each piece on a context (= stream) of its own; at most RUNNERS + 1 plans are
+    # alive.  RUNNERS = 1 by default: two pieces in flight at once (QC_PIPELINE_RUNNERS=2) were meant to fill each
+    # other's gaps -- the host round trips between the sweeps of a piece, the partly filled last wave of CTAs -- but
+    # measured 3 % SLOWER (1024 runs, np = 2048, nt = 1024: 5.33 s against 5.17 s of control loops): the CTAs of two
+    # sweeps interleave on the SMs, each sweep takes longer and the uploads of the producer queue behind both.
+    runners = max(1, int(os.environ.get("QC_PIPELINE_RUNNERS", "1")))
+    ctxs = [_eng.Context(local) for _ in range(runners + 2)]
     OT = ReportRootConfiguration.ReportFitterConfiguration.OutputType
     tm_["config_s"] = time.perf_counter() - t_mark
     work = []
     sm_count = ctxs[0].sm_count
     for shape, group in qbatch.plan_groups(shapes, mine).items():
         try:
-            # two plans are alive at a time (the running piece and the one being set up): 40 % of the free memory each
-            for chunk in memory_chunks(confs, group, ctxs[0].mem_info()[0], fraction=0.4):
+            for chunk in memory_chunks(confs, group, ctxs[0].mem_info()[0], fraction=0.8 / (runners + 1)):
                 c0 = confs[chunk[0]]
                 work += pipeline_pieces(chunk, int(c0.np), sm_count, c0.hamil_type == TaskRootConfiguration.HamilType.NTRIV)
         except MemoryError as e:
             print("An exception interrupted the jobs %s: %s" % (group, e), file=sys.stderr)
+    if len(work) <= 1:
+        runners = 1
+    alive = threading.Semaphore(runners + 1)
+    lock = threading.Lock()
+    t_pipe = time.perf_counter()
+    marks = {"first_ready": None, "first_run": None, "last_run": None}
 
     def prepare(k):
         """Host set-up of piece k (producer thread): per-run tasks and reporters, then the plan on this piece's context."""
-        idxs, ctx = work[k], ctxs[k % 2]
-        t0 = time.perf_counter()
-        pbs, reps = [], []
-        for i in idxs:
-            with qconfig.quiet():
-                tm = task_manager.create(confs[i])
-                rep_json = resolve_input_templates(variants[i], copy.deepcopy(data_rep))
-                ct, cp = ReportTableRootConfiguration(), ReportPlotRootConfiguration()
-                ct.load(rep_json)
-                cp.load(rep_json)
-            print_input(ct.fitter.out_path, confs[i], "table_inp_-1.txt")
-            reps.append(reporter.MultipleFitterReporter(ct.fitter, cp.fitter).open())
-            pbs.append(problem_from(confs[i], tm))
-        t1 = time.perf_counter()
-        grid = pbs[0].hamil == "ntriv"
-        b = (control.GridBatch if grid else control.NLevelBatch)(pbs, ctx=ctx)
-        if grid:
-            b.prewarm()
-        return idxs, pbs, reps, b, grid, t1 - t0, time.perf_counter() - t1
+        alive.acquire()
+        try:
+            idxs, ctx = work[k], ctxs[k % len(ctxs)]
+            t0 = time.perf_counter()
+            pbs, reps = [], []
+            for i in idxs:
+                with qconfig.quiet():
+                    tm = task_manager.create(confs[i])
+                    rep_json = resolve_input_templates(variants[i], copy.deepcopy(data_rep))
+                    ct, cp = ReportTableRootConfiguration(), ReportPlotRootConfiguration()
+                    ct.load(rep_json)
+                    cp.load(rep_json)
+                print_input(ct.fitter.out_path, confs[i], "table_inp_-1.txt")
+                reps.append(reporter.MultipleFitterReporter(ct.fitter, cp.fitter).open())
+                pbs.append(problem_from(confs[i], tm))
+            t1 = time.perf_counter()
+            grid = pbs[0].hamil == "ntriv"
+            b = (control.GridBatch if grid else control.NLevelBatch)(pbs, ctx=ctx)
+            if grid:
+                b.prewarm()
+            t2 = time.perf_counter()
+            with lock:
+                tm_["task_setup_s"] += t1 - t0
+                tm_["plan_setup_s"] += t2 - t1
+                tm_["plans"] += 1
+                if marks["first_ready"] is None:
+                    marks["first_ready"] = t2
+            return idxs, pbs, reps, b, grid, ctx
+        except BaseException:
+            alive.release()
+            raise
+
+    def consume(fut):
+        """Control loops and reports of one prepared piece (runner thread)."""
+        idxs, pbs, reps, b, grid, ctx = fut.result()          # a failed set-up has released its slot itself
+        try:
+            t_run = time.perf_counter()
+            with lock:
+                if marks["first_run"] is None:
+                    marks["first_run"] = t_run
+            if any(r.conf_rep_table.plotting_flag in (OT.ALL, OT.TABLES) for r in reps):
+                # per-step tables were asked for: instrument the resident states at the steps the tables keep
+                from .fitter import BatchObserver
+                akx = None
+                if grid:
+                    akx = numpy.ascontiguousarray((math_base.initak(pbs[0].np_, pbs[0].dx, 1, pbs[0].ntriv) *
+                                                   (phys_base.hart_to_cm / (-1j) / phys_base.dalt_to_au)).real)
+                b.plan.set_instr_grid(numpy.asarray(pbs[0].x, numpy.float64), akx)
+                b.observer = BatchObserver(b, reps)
+            tt = pbs[0].task_type
+            if tt == "optimal_control_krotov":
+                hist = b.run_krotov()
+            elif tt == "optimal_control_unit_transform":
+                tables_iter = str(data_rep.get("fitter", {}).get("plotting_flag", "")).lower() == "tables_iter"
+                hist = b.run_unit_transform(keep_fields=not tables_iter)
+            elif tt == "local_control_population":
+                hist = b.run_local_population()
+            elif tt == "local_control_projection":
+                hist = b.run_local_projection()
+            else:
+                hist = b.run_prescribed()
+            errors = getattr(b, "errors", [""] * len(idxs))
+            ctx.synchronize()
+            t_rep = time.perf_counter()
+            if b.observer is not None:
+                b.observer.close()
+            for j, i in enumerate(idxs):
+                results[i] = hist[j]
+                for r in hist[j]:
+                    reps[j].print_iter_point_fitter(r.it, r.goal_close, None if r.E_tlist is None else list(r.E_tlist),
+                                                    pbs[j].t_list, numpy.complex128(r.Fsm), numpy.float64(r.E_int), r.J,
+                                                    pbs[j].nt)
+                reps[j].close()
+                if errors[j] and verbose:
+                    print("An exception interrupted the job #%d: %s" % (i, errors[j]), file=sys.stderr)
+                elif verbose:
+                    print("Job #%d is done" % i)
+            t_end = time.perf_counter()
+            with lock:
+                tm_["report_s"] += t_end - t_rep
+                marks["last_run"] = max(marks["last_run"] or t_end, t_rep)
+        finally:
+            b.close()
+            alive.release()
 
     # Fresh device memory is expensive beside a running sweep (an allocation by the driver returns only when the sweep
-    # ends): while the GPU is still idle, reserve the working set of the pipeline -- two plans are alive at a time --
-    # as an arena of the library (qc_pool_reserve); it goes back when the last piece is done.
+    # ends): while the GPU is still idle, reserve the working set of the pipeline -- runners + 1 plans are alive at a
+    # time -- as an arena of the library (qc_pool_reserve); it goes back when the last piece is done.
     reserved = False
     if len(work) > 1:
         need = 0
@@ -269,66 +349,26 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True, 
             need = max(need, _eng.plan_footprint(_eng.HAMIL_NONTRIV if grid else _eng.HAMIL_BH_X, c0.np, c0.nlevs, c0.nb,
                                                  c0.fitter.propagation.nch, len(idxs), nt_max,
                                                  bool(c0.fitter.hf_hide) and grid, _NAMES.get(c0.task_type) in control.TRAJ_TASKS))
-        want = int(2.1 * need) + (64 << 20)
+        want = int((runners + 1.1) * need) + (64 << 20)
         if want <= 0.9 * ctxs[0].mem_info()[0]:
             try:
                 ctxs[0].pool_reserve(want)
                 reserved = True
             except Exception:
                 reserved = False
-    pool = concurrent.futures.ThreadPoolExecutor(1)
-    nxt = pool.submit(prepare, 0) if work else None
-    for k in range(len(work)):
-        t_mark = time.perf_counter()
-        idxs, pbs, reps, b, grid, t_task, t_plan = nxt.result()
-        tm_["setup_wait_s"] += time.perf_counter() - t_mark
-        tm_["task_setup_s"] += t_task
-        tm_["plan_setup_s"] += t_plan
-        tm_["plans"] += 1
-        nxt = pool.submit(prepare, k + 1) if k + 1 < len(work) else None
-        ctx = ctxs[k % 2]
-        t_mark = time.perf_counter()
-        if any(r.conf_rep_table.plotting_flag in (OT.ALL, OT.TABLES) for r in reps):
-            # per-step tables were asked for: instrument the resident states at the steps the tables keep
-            from .fitter import BatchObserver
-            akx = None
-            if grid:
-                akx = numpy.ascontiguousarray((math_base.initak(pbs[0].np_, pbs[0].dx, 1, pbs[0].ntriv) *
-                                               (phys_base.hart_to_cm / (-1j) / phys_base.dalt_to_au)).real)
-            b.plan.set_instr_grid(numpy.asarray(pbs[0].x, numpy.float64), akx)
-            b.observer = BatchObserver(b, reps)
-        tt = pbs[0].task_type
-        if tt == "optimal_control_krotov":
-            hist = b.run_krotov()
-        elif tt == "optimal_control_unit_transform":
-            tables_iter = str(data_rep.get("fitter", {}).get("plotting_flag", "")).lower() == "tables_iter"
-            hist = b.run_unit_transform(keep_fields=not tables_iter)
-        elif tt == "local_control_population":
-            hist = b.run_local_population()
-        elif tt == "local_control_projection":
-            hist = b.run_local_projection()
-        else:
-            hist = b.run_prescribed()
-        errors = getattr(b, "errors", [""] * len(idxs))
-        ctx.synchronize()
-        tm_["run_s"] += time.perf_counter() - t_mark
-        t_mark = time.perf_counter()
-        if b.observer is not None:
-            b.observer.close()
-        for j, i in enumerate(idxs):
-            results[i] = hist[j]
-            for r in hist[j]:
-                reps[j].print_iter_point_fitter(r.it, r.goal_close, None if r.E_tlist is None else list(r.E_tlist),
-                                                pbs[j].t_list, numpy.complex128(r.Fsm), numpy.float64(r.E_int), r.J,
-                                                pbs[j].nt)
-            reps[j].close()
-            if errors[j] and verbose:
-                print("An exception interrupted the job #%d: %s" % (i, errors[j]), file=sys.stderr)
-            elif verbose:
-                print("Job #%d is done" % i)
-        b.close()
-        tm_["report_s"] += time.perf_counter() - t_mark
-    pool.shutdown()
+    prep_pool = concurrent.futures.ThreadPoolExecutor(1)
+    run_pool = concurrent.futures.ThreadPoolExecutor(runners)
+    try:
+        preps = [prep_pool.submit(prepare, k) for k in range(len(work))]
+        runs = [run_pool.submit(consume, f) for f in preps]
+        for f in runs:
+            f.result()
+    finally:
+        prep_pool.shutdown(wait=True, cancel_futures=True)
+        run_pool.shutdown(wait=True, cancel_futures=True)
+    if work:
+        tm_["setup_wait_s"] = (marks["first_run"] or t_pipe) - t_pipe       # what the GPU waited for before its first sweep
+        tm_["run_s"] = (marks["last_run"] or t_pipe) - (marks["first_run"] or t_pipe)
     if reserved:
         ctxs[0].pool_reserve(0)
     for ctx in ctxs:
