@@ -421,7 +421,7 @@ def ut_jx_tsweep_block(ctx, rank, world, iterations, cpu):
 # ------------------------------------------------------------------------------------------------
 def e2e_api_block(rank, world, local_dev, runs, nt):
     """newcheb.run_variants (the body of ``python newcheb.py --json_task ... --json_rep ...``, newcheb.py:641-975) on a
-    "@SUBST:LIST" template of ``runs`` two-level Krotov variants at np = 2048 (amplitude x pulse centre), from JSON
+    "@SUBST:LIST" template of ``runs`` two-level Krotov variants at np = 2048 (amplitude x pulse centre; 1184 = 32 x 37), from JSON
     dictionaries to the gathered final rows: wall clock INCLUDING configuration, task_manager.create, Newton tables,
     exp_L / field tables, plan upload, the control loops (iteration 0 + 1 Krotov iteration) and the report files."""
     import tempfile
@@ -429,8 +429,8 @@ def e2e_api_block(rank, world, local_dev, runs, nt):
     from qcontrol_b200 import batch, newcheb
     dt = 350e-15 / 230000
     T = dt * nt
-    n_e0 = int(round(math.sqrt(runs)))
-    n_t0 = (runs + n_e0 - 1) // n_e0
+    n_e0 = max(d for d in range(1, int(math.sqrt(runs)) + 1) if runs % d == 0)      # runs = n_e0 x n_t0 exactly
+    n_t0 = runs // n_e0
     tpl = {"task_type": "optimal_control_krotov", "pot_type": "morse", "wf_type": "morse", "hamil_type": "ntriv",
            "init_guess": "gauss", "init_guess_hf": "exp", "nb": 1, "nlevs": 2, "T": T, "L": 5.0, "np": NP_, "a": 1.0,
            "De": 20000.0, "x0p": -0.17, "a_e": 1.0, "De_e": 10000.0, "Du": 20000.0,
@@ -672,7 +672,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the ut_jx_tsweep and e2e_api blocks")
     ap.add_argument("--ut-iterations", type=int, default=10)
-    ap.add_argument("--api-runs", type=int, default=1024)
+    ap.add_argument("--api-runs", type=int, default=1184,
+                    help="variants of the e2e_api template: 8 x 148, whole waves of CTAs on 1, 2, 4 and 8 GPUs")
     ap.add_argument("--api-nt", type=int, default=1024)
     a = ap.parse_args()
     if a.impl == "reference":

@@ -235,11 +235,15 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True, 
     tm_["config_s"] = time.perf_counter() - t_mark
     work = []
     sm_count = ctxs[0].sm_count
+    free_bytes = ctxs[0].mem_info()[0]
     for shape, group in qbatch.plan_groups(shapes, mine).items():
         try:
-            for chunk in memory_chunks(confs, group, ctxs[0].mem_info()[0], fraction=0.8 / (runners + 1)):
-                c0 = confs[chunk[0]]
-                work += pipeline_pieces(chunk, int(c0.np), sm_count, c0.hamil_type == TaskRootConfiguration.HamilType.NTRIV)
+            # whole waves first (longest runs first, like memory_chunks orders them), then the memory budget per piece:
+            # runners + 1 plans are alive at a time, so it is the PIECE that has to fit its share of the free memory
+            c0 = confs[group[0]]
+            order = sorted(group, key=lambda i: (-int(confs[i].fitter.propagation.nt), i))
+            for piece in pipeline_pieces(order, int(c0.np), sm_count, c0.hamil_type == TaskRootConfiguration.HamilType.NTRIV):
+                work += memory_chunks(confs, piece, free_bytes, fraction=0.8 / (runners + 1))
         except MemoryError as e:
             print("An exception interrupted the jobs %s: %s" % (group, e), file=sys.stderr)
     if len(work) <= 1:
