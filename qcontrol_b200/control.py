@@ -220,6 +220,7 @@ class _BatchBase:
             self.poly_orders[direction] = math_base.truncation_order(nch, dvs, self.poly_tol)
             self.plan.set_poly_orders(slot, self.poly_orders[direction])
 
+    on_last_sweep = None  # callable() invoked once the last sweep of a control loop has been launched (run_krotov)
     time_sweeps = False  # accumulate CUDA-event time of the sweep launches in sweep_ms (synchronises)
     sweep_ms = 0.0
     observer = None      # callable(prop_id, l, direction, snapshots) invoked at l = 0 and every `stride` steps
@@ -489,6 +490,13 @@ class GridBatch(_BatchBase):
             else:
                 self._sweep("iter_%df" % it, FORWARD, (0, 1), 0, eng.FIELD_KROTOV_FWD, 0, self.nt_max + 1, 1, 0)
                 E0s = None
+            # For it >= 1 every stopping decision below is independent of this sweep's results (the reference tests
+            # its loop condition on a zeroed goal_close_vec): if no run goes on, the sweep just launched is the last
+            # GPU work of this batch -- a batch entry point may start the next batch's sweeps behind it right now
+            if it >= 1 and self.observer is None and self.on_last_sweep is not None:
+                limits = [p.iter_max if iter_max is None else iter_max for p in self.pbs]
+                if all(done[b] or (lim != -1 and it >= lim) for b, lim in enumerate(limits)):
+                    self.on_last_sweep()
             if E0s is None:
                 E0s = pl.get_fields()[:, 0]
             rows, gc = self._finish_forward(it, E0s)

@@ -223,13 +223,15 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True, 
                        bool(conf.fitter.hf_hide), conf.task_type, float(conf.L), float(conf.fitter.propagation.m)))
     mine = qbatch.lpt_shards(costs, world)[rank]
     results = {}
-    # Pipeline: ONE producer thread sets pieces up (tasks, reporters, plan upload), RUNNERS runner threads drive the
-    # control loops of consecutive pieces, each piece on a context (= stream) of its own; at most RUNNERS + 1 plans are
-    # alive.  RUNNERS = 1 by default: two pieces in flight at once (QC_PIPELINE_RUNNERS=2) were meant to fill each
-    # other's gaps -- the host round trips between the sweeps of a piece, the partly filled last wave of CTAs -- but
-    # measured 3 % SLOWER (1024 runs, np = 2048, nt = 1024: 5.33 s against 5.17 s of control loops): the CTAs of two
-    # sweeps interleave on the SMs, each sweep takes longer and the uploads of the producer queue behind both.
-    runners = max(1, int(os.environ.get("QC_PIPELINE_RUNNERS", "1")))
+    # Pipeline: ONE producer thread sets pieces up (tasks, reporters, plan upload), two runner threads drive the control
+    # loops of consecutive pieces, each piece on a context (= stream) of its own; at most RUNNERS + 1 plans are alive.
+    # The runners are GATED: piece k + 1 starts when piece k has launched its last sweep (GridBatch.on_last_sweep; for
+    # control loops without that hook: when piece k is finished), so its first sweep queues behind the last one of
+    # piece k and the host work that ends a piece (final overlaps, tables, report files) costs the GPU nothing.  Two
+    # pieces in flight without the gate were measured 3 % SLOWER than one (1024 runs, np = 2048, nt = 1024: 5.33 s
+    # against 5.17 s of control loops): the CTAs of two sweeps interleave on the SMs and each sweep takes longer.
+    # QC_PIPELINE_RUNNERS=1: strictly one piece after the other.
+    runners = max(1, min(2, int(os.environ.get("QC_PIPELINE_RUNNERS", "2"))))
     ctxs = [_eng.Context(local) for _ in range(runners + 2)]
     OT = ReportRootConfiguration.ReportFitterConfiguration.OutputType
     tm_["config_s"] = time.perf_counter() - t_mark
@@ -250,6 +252,7 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True, 
         runners = 1
     alive = threading.Semaphore(runners + 1)
     lock = threading.Lock()
+    gates = [threading.Event() for _ in work]           # gates[k]: piece k has launched its last sweep (or is done)
     t_pipe = time.perf_counter()
     marks = {"first_ready": None, "first_run": None, "last_run": None}
 
@@ -287,10 +290,17 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True, 
             alive.release()
             raise
 
-    def consume(fut):
+    def consume(k, fut):
         """Control loops and reports of one prepared piece (runner thread)."""
-        idxs, pbs, reps, b, grid, ctx = fut.result()          # a failed set-up has released its slot itself
         try:
+            idxs, pbs, reps, b, grid, ctx = fut.result()      # a failed set-up has released its slot itself
+        except BaseException:
+            gates[k].set()
+            raise
+        try:
+            if k > 0:
+                gates[k - 1].wait()
+            b.on_last_sweep = gates[k].set
             t_run = time.perf_counter()
             with lock:
                 if marks["first_run"] is None:
@@ -337,6 +347,7 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True, 
                 tm_["report_s"] += t_end - t_rep
                 marks["last_run"] = max(marks["last_run"] or t_end, t_rep)
         finally:
+            gates[k].set()
             b.close()
             alive.release()
 
@@ -364,7 +375,7 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True, 
     run_pool = concurrent.futures.ThreadPoolExecutor(runners)
     try:
         preps = [prep_pool.submit(prepare, k) for k in range(len(work))]
-        runs = [run_pool.submit(consume, f) for f in preps]
+        runs = [run_pool.submit(consume, k, f) for k, f in enumerate(preps)]
         for f in runs:
             f.result()
     finally:
