@@ -204,8 +204,8 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True, 
     import concurrent.futures
     import threading
     import time
-    tm_ = {"config_s": 0.0, "task_setup_s": 0.0, "plan_setup_s": 0.0, "setup_wait_s": 0.0, "run_s": 0.0, "report_s": 0.0,
-           "plans": 0}
+    tm_ = {"config_s": 0.0, "reserve_s": 0.0, "task_setup_s": 0.0, "plan_setup_s": 0.0, "setup_wait_s": 0.0, "run_s": 0.0,
+           "report_s": 0.0, "teardown_s": 0.0, "plans": 0}
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0")) if device is None else device
@@ -237,6 +237,7 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True, 
     tm_["config_s"] = time.perf_counter() - t_mark
     work = []
     sm_count = ctxs[0].sm_count
+    t_mark = time.perf_counter()
     free_bytes = ctxs[0].mem_info()[0]
     for shape, group in qbatch.plan_groups(shapes, mine).items():
         try:
@@ -253,7 +254,6 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True, 
     alive = threading.Semaphore(runners + 1)
     lock = threading.Lock()
     gates = [threading.Event() for _ in work]           # gates[k]: piece k has launched its last sweep (or is done)
-    t_pipe = time.perf_counter()
     marks = {"first_ready": None, "first_run": None, "last_run": None}
 
     def prepare(k):
@@ -371,6 +371,8 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True, 
                 reserved = True
             except Exception:
                 reserved = False
+    tm_["reserve_s"] = time.perf_counter() - t_mark          # cached blocks back to the driver, pieces planned, arena reserved
+    t_pipe = time.perf_counter()
     prep_pool = concurrent.futures.ThreadPoolExecutor(1)
     run_pool = concurrent.futures.ThreadPoolExecutor(runners)
     try:
@@ -384,10 +386,12 @@ def run_variants(variants, data_rep, seed_base=1000, device=None, verbose=True, 
     if work:
         tm_["setup_wait_s"] = (marks["first_run"] or t_pipe) - t_pipe       # what the GPU waited for before its first sweep
         tm_["run_s"] = (marks["last_run"] or t_pipe) - (marks["first_run"] or t_pipe)
+    t_mark = time.perf_counter()
     if reserved:
         ctxs[0].pool_reserve(0)
     for ctx in ctxs:
         ctx.close()
+    tm_["teardown_s"] = time.perf_counter() - t_mark          # arena and contexts released
     if timings is not None:
         timings.update(tm_)
     return results
