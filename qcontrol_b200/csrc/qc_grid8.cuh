@@ -2,11 +2,14 @@
 // (qc_grid.cuh; Hamil2DNonTrivial, hamil_2d.py:34-73; prop_cpu, phys_base.py:129-178), laid out for FOUR warps per
 // scheduler instead of two.
 //
-// Why.  The 256-thread forms hold 16 grid points per thread in 255 registers, i.e. two warps per scheduler: the FP64
-// pipe is 72 % busy whatever the grid size or the barrier structure (profiles/r02b_*), because two warps cannot cover
-// each other's shared-memory round trips.  Here a thread owns EIGHT points (128 registers), a level is eight warps,
-// a CTA sixteen.  Eight points per thread mean a four-pass transform (8 x 8 x 8 x 4) with three exchanges per
-// direction instead of two; shared memory could not carry that (12 accesses per point and order against 8), so two of
+// EXPERIMENTAL (QC_GRID_VAR=2), kept as the measured answer to "why not more warps": parity-green and SLOWER than the
+// 256-thread form (0.549 against 0.615 of the FP64 peak).
+//
+// Why it was built.  The 256-thread forms hold 16 grid points per thread in 255 registers, i.e. two warps per
+// scheduler, and keep the FP64 pipe 72 % busy whatever the grid size or the barrier structure (profiles/r02b_*).
+// Here a thread owns EIGHT points (124 registers), a level is eight warps, a CTA sixteen.  Eight points per thread
+// mean a four-pass transform (8 x 8 x 8 x 4) with three exchanges per direction instead of two; shared memory could
+// not carry that (12 accesses per point and order against 8), so two of
 // the three exchanges go through TENSOR MEMORY, whose load / store shapes differ in how they map threads to lanes:
 //   tcgen05.st.32x32b   thread i  <-> lane i, consecutive columns
 //   tcgen05.ld.16x256b  thread 4a + b <-> lanes a and a + 8, column pairs 2b, 2b+1 of every eight columns
@@ -34,6 +37,11 @@
 //
 // Covers what the bench path needs: prescribed and Krotov field laws, rotating frame, renormalisation, trajectory in /
 // out.  Local control, the one-step / operator entry points and small batches keep the 256-thread forms.
+//
+// What it showed (profiles/r02k_*, r02u_*): more warps cover latency, they do not create issue slots.  A scheduler issues
+// one instruction per cycle and does not prefer FP64 work; this form needs 0.54 non-FP64 instructions per FP64
+// instruction (table loads from shared memory, register moves into sixteen-register tcgen05 operands, per-thread fixed
+// costs over eight points) against 0.34 of the 256-thread form, and its pipe is 65 % busy with ready warps waiting.
 #pragma once
 #include "qc_grid.cuh"
 

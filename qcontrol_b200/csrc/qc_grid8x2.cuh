@@ -3,9 +3,9 @@
 // INDEPENDENT phases instead of two.  A level of 1024 points is four warps, one per scheduler (= one per tensor-memory
 // lane quadrant); two runs = four levels = sixteen warps, and the four warps of a scheduler belong to four different
 // levels that meet nobody but their own level (two level barriers per order) and their partner level (the phi
-// hand-over, one order of slack).  qc_grid8.cuh at np = 2048 showed why that matters: with eight warps per level the
-// four warps of a scheduler are two pairs in lock step, i.e. still two phases, and the FP64 pipe stays where the
-// 256-thread forms leave it.
+// hand-over, one order of slack).  EXPERIMENTAL (QC_GRID_VAR=2 at np = 1024): it was built to test whether the lock
+// step of the eight warps of a level is what holds qc_grid8.cuh back at np = 2048.  It is not: parity-green, 0.562
+// against 0.621 of the default two-runs-per-CTA form -- the issue port is.
 //
 // Transform: N = 1024 = 8 x 8 x 4 x 4, n = 128 n1 + 16 n2 + 4 n3 + n4, k = k1 + 8 k2 + 64 k3 + 256 k4; thread T = 32 q + L.
 //   x layout   registers n1;          thread: n2 = T >> 4, n3 = (L >> 2) & 3, n4 = L & 3            (x = T + 128 n1)
